@@ -1,0 +1,88 @@
+"""ctypes binding of libgdr.so (the C ABI declared in include/gdr.h).
+
+There is no fallback: if the CUDA library cannot be loaded (and cannot be built
+because nvcc is absent) importing the rasterizer raises.  The product path never
+routes through a CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_vp = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+_f = C.c_float
+_pi64 = C.POINTER(C.c_int64)
+
+GDR_OK = 0
+GRAD_MEANS2D, GRAD_MEANS3D, GRAD_COLOR, GRAD_OPACITY, GRAD_COV, GRAD_ALL = 1, 2, 4, 8, 16, 31
+
+# name -> (restype, argtypes); must list every symbol include/gdr.h declares
+SIGNATURES = {
+    "gdr_abi_version": (_i, []),
+    "gdr_last_error": (C.c_char_p, []),
+    "gdr_geom_state_bytes": (_i, [_i, _pi64]),
+    "gdr_image_state_bytes": (_i, [_i, _i, _pi64]),
+    "gdr_splat_stream_bytes": (_i, [_i64, _pi64]),
+    "gdr_sort_scratch_bytes": (_i, [_i64, _pi64]),
+    "gdr_backward_scratch_bytes": (_i, [_i, _pi64]),
+    "gdr_forward_project": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _i,
+                                 _vp, _vp, _vp, _vp, _vp]),
+    "gdr_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "gdr_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp,
+                          _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gdr_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
+    "gdr_debug_unpack_geom": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gdr_debug_unpack_bins": (_i, [_i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class GdrError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building in-tree first if the sources are newer) and type the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.isfile(path) or (os.path.isfile(_build.NVCC) and not _build.is_fresh()):
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc, or a compile error: fail loudly
+            if not os.path.isfile(path):
+                raise GdrError(
+                    "libgdr.so (the CUDA rasterizer) is not built and could not be built: "
+                    f"{e}. Run `python -m generativedensification_b200.build`.") from e
+            raise
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.gdr_abi_version() != 1:
+        raise GdrError(f"libgdr.so ABI version {lib.gdr_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != GDR_OK:
+        msg = load().gdr_last_error()
+        raise GdrError(f"{what} failed ({status}): {msg.decode() if msg else ''}")
+
+
+def query_bytes(fn_name: str, *args) -> int:
+    out = C.c_int64(0)
+    check(getattr(load(), fn_name)(*args, C.byref(out)), fn_name)
+    return int(out.value)

@@ -1,0 +1,244 @@
+// Stage 2: tile binning and per-tile depth sort.
+//
+// Replaces the reference's InclusiveSum + duplicateWithKeys + global 64-bit
+// DeviceRadixSort + identifyTileRanges (RAST/cuda_rasterizer/rasterizer_impl.cu:
+// 278, 70-111, 304-309, 116-138).  The order contract is unchanged: inside a
+// tile, instances are ordered by (view-depth bits ascending, Gaussian index
+// ascending) -- exactly what the reference's stable LSD sort on
+// (tile << 32 | depth bits) of idx-major emitted pairs yields.
+//
+// B200-first structure:
+//   tile_scan   one CTA scans the per-tile bin counters filled by the project
+//               kernel -> tile_offsets (the reference's `ranges`), R.
+//   emit        warp-cooperative walk over (Gaussian, tile) pairs; one
+//               aggregated atomic per distinct tile claims slots in the tile's
+//               segment; writes the key (depth bits << 32 | idx).  Slot order
+//               within a segment is arbitrary -- the keys are unique, so the
+//               sort below makes the result deterministic.
+//   tile_sort   one CTA per tile sorts its segment in shared memory (bitonic on
+//               u64; segments longer than the smem chunk are chunk-sorted and
+//               merged through global memory) and writes the tile's depth-sorted
+//               48-byte Splat records contiguously, ready for bulk-copy staging
+//               in the blend kernels.
+// Compared with a global 64-bit radix sort of all R pairs (6+ passes over
+// 12 B/pair), each instance is written once as an 8-byte key and read once.
+#include "kernels.h"
+#include "tile_iter.cuh"
+
+namespace gdr {
+
+namespace {
+
+constexpr int SCAN_THREADS = 1024;
+
+__global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageState img) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t warp_max[32];
+    const int tid = threadIdx.x;
+    const int per = (T + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int b = min(T, tid * per), e = min(T, b + per);
+    uint32_t local = 0, lmax = 0;
+    for (int i = b; i < e; i++) {
+        const uint32_t c = img.tile_counter[i];
+        local += c;
+        lmax = max(lmax, c);
+    }
+    // block exclusive scan of `local`
+    const int lane = tid & 31, wid = tid >> 5;
+    int incl = warp_incl_scan((int)local);
+    uint32_t m = lmax;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if (lane == 31) warp_sums[wid] = (uint32_t)incl;
+    if (lane == 0) warp_max[wid] = m;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t v = warp_sums[lane];
+        const int s = warp_incl_scan((int)v);
+        warp_sums[lane] = (uint32_t)s - v;  // exclusive
+        uint32_t mm = warp_max[lane];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mm = max(mm, __shfl_xor_sync(0xffffffffu, mm, d));
+        if (lane == 31) {
+            img.header[HDR_NUM_RENDERED] = (uint32_t)s;
+            img.tile_offsets[T] = (uint32_t)s;
+        }
+        if (lane == 0) img.header[HDR_MAX_TILE] = mm;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[wid] + (uint32_t)incl - local;
+    for (int i = b; i < e; i++) {
+        const uint32_t c = img.tile_counter[i];
+        img.tile_offsets[i] = run;
+        img.tile_counter[i] = 0;  // becomes the emit cursor
+        run += c;
+    }
+}
+
+constexpr int EMIT_THREADS = 128;
+
+__global__ void __launch_bounds__(EMIT_THREADS)
+emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii, const Splat* __restrict__ splat,
+            const uint32_t* __restrict__ tile_offsets, uint32_t* __restrict__ cursor, uint64_t* __restrict__ keys,
+            uint32_t* __restrict__ header, int64_t capacity) {
+    const int idx = blockIdx.x * EMIT_THREADS + threadIdx.x;
+    int n = 0, x0 = 0, y0 = 0, w = 0;
+    uint32_t depth_bits = 0;
+    if (idx < P) {
+        const int r = radii[idx];
+        if (r > 0) {
+            const float4 q0 = __ldg(&splat[idx].q0);
+            int x1, y1;
+            tile_rect(q0.x, q0.y, r, gx, gy, x0, y0, x1, y1);
+            w = x1 - x0;
+            n = w * (y1 - y0);
+            depth_bits = __float_as_uint(q0.z);
+        }
+    }
+    const int lane = (int)lane_id();
+    bool overflow = false;
+    warp_foreach_tile(n, x0, y0, w, gx, [&](int tile, int owner, int, bool valid, unsigned active) {
+        const uint32_t o_depth = __shfl_sync(0xffffffffu, depth_bits, owner);
+        const int o_idx = __shfl_sync(0xffffffffu, idx, owner);
+        if (valid) {
+            const unsigned peers = __match_any_sync(active, tile);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&cursor[tile], (unsigned)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const uint64_t pos = (uint64_t)__ldg(&tile_offsets[tile]) + base + __popc(peers & lanemask_lt());
+            if ((int64_t)pos < capacity)
+                keys[pos] = ((uint64_t)o_depth << 32) | (uint32_t)o_idx;
+            else
+                overflow = true;
+        }
+    });
+    if (overflow) atomicOr(&header[HDR_OVERFLOW], 1u);
+}
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_CHUNK = 4096;  // keys per shared-memory sort (32 KB)
+
+// Bitonic sort of s[0 .. n_pad) ascending; n_pad is a power of two; all threads call.
+__device__ __forceinline__ void bitonic_sort_smem(uint64_t* s, int n_pad) {
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (n_pad >> 1); i += SORT_THREADS) {
+                const int a = 2 * i - (i & (j - 1));
+                const int b = a + j;
+                const uint64_t va = s[a], vb = s[b];
+                const bool up = (a & k) == 0;
+                if ((va > vb) == up) {
+                    s[a] = vb;
+                    s[b] = va;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int lower_bound_u64(const uint64_t* a, int n, uint64_t key) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+tile_sort_kernel(const Splat* __restrict__ splat, const uint32_t* __restrict__ tile_offsets,
+                 uint32_t* __restrict__ cursor, uint64_t* keys, uint64_t* keys_alt, Splat* __restrict__ stream,
+                 int64_t capacity) {
+    __shared__ uint64_t s_keys[SORT_CHUNK];
+    const int tile = blockIdx.x;
+    if (threadIdx.x == 0) cursor[tile] = 0;  // leave the bin cursors clean for a (speculative) re-run
+    const int64_t b = min((int64_t)tile_offsets[tile], capacity);
+    const int64_t e = min((int64_t)tile_offsets[tile + 1], capacity);
+    const int n = (int)(e - b);
+    if (n == 0) return;
+    uint64_t* seg = keys + b;
+    const uint64_t* sorted;  // where the sorted keys end up (shared or global)
+
+    if (n <= SORT_CHUNK) {
+        int n_pad = 2;
+        while (n_pad < n) n_pad <<= 1;
+        for (int i = threadIdx.x; i < n_pad; i += SORT_THREADS) s_keys[i] = i < n ? seg[i] : ~0ull;
+        __syncthreads();
+        bitonic_sort_smem(s_keys, n_pad);
+        sorted = s_keys;
+    } else {
+        // chunk sort in shared memory, written back in place
+        for (int c0 = 0; c0 < n; c0 += SORT_CHUNK) {
+            const int cn = min(SORT_CHUNK, n - c0);
+            for (int i = threadIdx.x; i < SORT_CHUNK; i += SORT_THREADS) s_keys[i] = i < cn ? seg[c0 + i] : ~0ull;
+            __syncthreads();
+            bitonic_sort_smem(s_keys, SORT_CHUNK);
+            for (int i = threadIdx.x; i < cn; i += SORT_THREADS) seg[c0 + i] = s_keys[i];
+            __syncthreads();
+        }
+        // pairwise merges through global memory (keys are unique, so ranks are unambiguous)
+        uint64_t* src = seg;
+        uint64_t* dst = keys_alt + b;
+        for (int width = SORT_CHUNK; width < n; width <<= 1) {
+            __threadfence_block();
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+                const int pair0 = (i / (2 * width)) * (2 * width);
+                const int mid = min(n, pair0 + width), end = min(n, pair0 + 2 * width);
+                const uint64_t k = src[i];
+                int pos;
+                if (i < mid)
+                    pos = i + lower_bound_u64(src + mid, end - mid, k);
+                else
+                    pos = (i - mid) + pair0 + lower_bound_u64(src + pair0, mid - pair0, k);
+                dst[pos] = k;
+            }
+            uint64_t* t = src;
+            src = dst;
+            dst = t;
+        }
+        __threadfence_block();
+        __syncthreads();
+        sorted = src;
+    }
+
+    // gather the Gaussians' records into the tile's contiguous, depth-ordered stream
+    Splat* out = stream + b;
+    for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+        const uint32_t id = (uint32_t)(sorted[i] & 0xffffffffu);
+        const float4* src4 = reinterpret_cast<const float4*>(splat + id);
+        const float4 a0 = __ldg(src4), a1 = __ldg(src4 + 1), a2 = __ldg(src4 + 2);
+        float4* dst4 = reinterpret_cast<float4*>(out + i);
+        dst4[0] = a0;
+        dst4[1] = a1;
+        dst4[2] = a2;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_tile_scan(int T, ImageState img, cudaStream_t s) {
+    tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(T, img);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_emit(int P, int W, int H, const int32_t* radii, GeomState geom, ImageState img, uint64_t* keys,
+                        int64_t capacity, cudaStream_t s) {
+    if (P <= 0) return cudaSuccess;
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    emit_kernel<<<(P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(
+        P, gx, gy, radii, geom.splat, img.tile_offsets, img.tile_counter, keys, img.header, capacity);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint64_t* keys, uint64_t* keys_alt,
+                             Splat* stream, int64_t capacity, cudaStream_t s) {
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    tile_sort_kernel<<<gx * gy, SORT_THREADS, 0, s>>>(geom.splat, img.tile_offsets, img.tile_counter, keys, keys_alt,
+                                                     stream, capacity);
+    return cudaGetLastError();
+}
+
+}  // namespace gdr

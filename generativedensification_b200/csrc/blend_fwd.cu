@@ -1,0 +1,133 @@
+// Stage 3: forward alpha blend (front to back), one CTA per 16x16 tile.
+//
+// Replaces the reference's renderCUDA forward (RAST/cuda_rasterizer/forward.cu:
+// 261-381).  Per pixel the arithmetic and its order are the reference's: the
+// same exponent expression, full-precision expf, alpha = min(0.99, o*G), skip
+// below 1/255, stop (without blending) when T*(1-alpha) < 1e-4, and
+// out_alpha = sum(alpha*T).  What differs is how the data gets there:
+//   * the tile's depth-sorted Splat records are contiguous (binning.cu), so each
+//     256-record chunk is staged with ONE cp.async.bulk (TMA engine) into a
+//     double-buffered shared-memory ring with mbarrier completion, while the
+//     previous chunk is blended; the reference gathers 28 B per record through
+//     per-thread loads and re-reads colour and depth from global memory for
+//     every contributing (pixel, Gaussian) pair;
+//   * a warp covers an 8x4 pixel block (not 16x2) so whole-warp rejects are more
+//     likely, and a per-record conservative threshold on the exponent skips the
+//     expf for pairs that cannot reach alpha = 1/255 (exact: the slack is far
+//     larger than any rounding error, and everything near the threshold still
+//     takes the reference's exact test).
+#include "kernels.h"
+
+namespace gdr {
+
+namespace {
+
+constexpr int BLEND_THREADS = 256;
+constexpr int CHUNK = 256;
+
+__global__ void __launch_bounds__(BLEND_THREADS)
+blend_forward_kernel(int W, int H, int gx, const float* __restrict__ bg, const uint32_t* __restrict__ tile_offsets,
+                     const Splat* __restrict__ stream, int64_t capacity, uint32_t* __restrict__ n_contrib,
+                     float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha) {
+    __shared__ __align__(128) Splat buf[2][CHUNK];
+    __shared__ __align__(8) uint64_t full[2];
+
+    const int tile = blockIdx.x;
+    const int tile_x = tile % gx, tile_y = tile / gx;
+    const int64_t rb = min((int64_t)tile_offsets[tile], capacity);
+    const int64_t re = min((int64_t)tile_offsets[tile + 1], capacity);
+    const int n = (int)(re - rb);
+    const int n_chunks = (n + CHUNK - 1) / CHUNK;
+    const Splat* src = stream + rb;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * TILE + (warp & 1) * 8 + (lane & 7);
+    const int py = tile_y * TILE + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < W && py < H;
+    const float2 pixf = make_float2((float)px, (float)py);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && n_chunks > 0) {
+        const uint32_t bytes = (uint32_t)(min(CHUNK, n) * sizeof(Splat));
+        mbar_expect_tx(&full[0], bytes);
+        bulk_g2s(&buf[0][0], src, bytes, &full[0]);
+    }
+
+    bool done = !inside;
+    float T = 1.0f;
+    float C0 = 0.f, C1 = 0.f, C2 = 0.f, weight = 0.f, D = 0.f;
+    uint32_t contributor = 0, last_contributor = 0;
+
+    int c = 0;
+    for (; c < n_chunks; c++) {
+        // prefetch the next chunk into the other buffer (its previous contents were
+        // released by the barrier at the end of the previous iteration)
+        if (threadIdx.x == 0 && c + 1 < n_chunks) {
+            const int cnt1 = min(CHUNK, n - (c + 1) * CHUNK);
+            const uint32_t bytes = (uint32_t)(cnt1 * sizeof(Splat));
+            mbar_expect_tx(&full[(c + 1) & 1], bytes);
+            bulk_g2s(&buf[(c + 1) & 1][0], src + (size_t)(c + 1) * CHUNK, bytes, &full[(c + 1) & 1]);
+        }
+        mbar_wait(&full[c & 1], (c >> 1) & 1);
+        const int cnt = min(CHUNK, n - c * CHUNK);
+        const Splat* sp = &buf[c & 1][0];
+        contributor = (uint32_t)(c * CHUNK);
+        for (int j = 0; !done && j < cnt; j++) {
+            contributor++;
+            const float4 q0 = sp[j].q0;
+            const float4 con_o = sp[j].q1;
+            const float2 d = make_float2(q0.x - pixf.x, q0.y - pixf.y);
+            const float power = pair_power(con_o, d.x, d.y);
+            if (power > 0.0f) continue;
+            const float4 q2 = sp[j].q2;
+            if (power < q2.w) continue;  // certainly alpha < 1/255
+            const float alpha = min(0.99f, con_o.w * expf(power));
+            if (alpha < ALPHA_MIN) continue;
+            const float test_T = T * (1 - alpha);
+            if (test_T < T_MIN) {
+                done = true;
+                continue;
+            }
+            C0 += q2.x * alpha * T;
+            C1 += q2.y * alpha * T;
+            C2 += q2.z * alpha * T;
+            weight += alpha * T;
+            D += q0.z * alpha * T;
+            T = test_T;
+            last_contributor = contributor;
+        }
+        // everyone is finished with buf[c & 1]; also the tile-wide early exit
+        if (__syncthreads_and(done)) break;
+    }
+    // never leave with a bulk copy still in flight into our shared memory
+    if (threadIdx.x == 0 && c < n_chunks && c + 1 < n_chunks) mbar_wait(&full[(c + 1) & 1], ((c + 1) >> 1) & 1);
+
+    if (inside) {
+        const size_t HW = (size_t)H * W;
+        const size_t pid = (size_t)py * W + px;
+        n_contrib[pid] = last_contributor;
+        out_color[pid] = C0 + T * __ldg(bg);
+        out_color[HW + pid] = C1 + T * __ldg(bg + 1);
+        out_color[2 * HW + pid] = C2 + T * __ldg(bg + 2);
+        out_alpha[pid] = weight;
+        out_depth[pid] = D;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_blend_forward(int W, int H, const float* bg, ImageState img, const Splat* stream,
+                                 int64_t capacity, float* out_color, float* out_depth, float* out_alpha,
+                                 cudaStream_t s) {
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    blend_forward_kernel<<<gx * gy, BLEND_THREADS, 0, s>>>(W, H, gx, bg, img.tile_offsets, stream, capacity,
+                                                           img.n_contrib, out_color, out_depth, out_alpha);
+    return cudaGetLastError();
+}
+
+}  // namespace gdr

@@ -1,0 +1,88 @@
+// Host-side launchers of the sm_100a kernels (one translation unit per stage).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "state.cuh"
+
+namespace gdr {
+
+struct ProjectArgs {
+    int P, sh_degree, M, W, H, gx, gy;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* opacities;
+    const float* scales;
+    float scale_modifier;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    float tan_fovx, tan_fovy, focal_x, focal_y;
+    int prefiltered;
+    int32_t* radii;
+    GeomState geom;
+    ImageState img;
+};
+
+// project.cu: per-Gaussian projection + warp-aggregated tile counting
+cudaError_t launch_project(const ProjectArgs& a, cudaStream_t s);
+cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
+                                cudaStream_t s);
+
+// binning.cu: tile scan, instance emission, per-tile depth sort + record gather
+cudaError_t launch_tile_scan(int T, ImageState img, cudaStream_t s);
+cudaError_t launch_emit(int P, int W, int H, const int32_t* radii, GeomState geom, ImageState img, uint64_t* keys,
+                        int64_t capacity, cudaStream_t s);
+cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint64_t* keys, uint64_t* keys_alt,
+                             Splat* stream, int64_t capacity, cudaStream_t s);
+
+// blend_fwd.cu
+cudaError_t launch_blend_forward(int W, int H, const float* bg, ImageState img, const Splat* stream,
+                                 int64_t capacity, float* out_color, float* out_depth, float* out_alpha,
+                                 cudaStream_t s);
+
+// blend_bwd.cu: accum is [P][12] floats: (mean2D x,y,|x|,|y|), (conic a,b,c, opacity), (r,g,b, depth)
+cudaError_t launch_blend_backward(int W, int H, const float* bg, ImageState img, const Splat* stream,
+                                  int64_t capacity, const float* out_alpha, const float* dL_dcolor,
+                                  const float* dL_ddepth, const float* dL_dalpha, float* accum, int grad_mask,
+                                  cudaStream_t s);
+
+struct GaussBackwardArgs {
+    int P, sh_degree, M, W, H;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* scales;
+    float scale_modifier;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    float tan_fovx, tan_fovy, focal_x, focal_y;
+    const int32_t* radii;
+    GeomState geom;
+    const float* accum;
+    int grad_mask;
+    float* dL_dmeans2D;
+    float* dL_dcolors;
+    float* dL_dopacity;
+    float* dL_dmeans3D;
+    float* dL_dcov3D;
+    float* dL_dsh;
+    float* dL_dscales;
+    float* dL_drotations;
+};
+// gauss_bwd.cu: fused per-Gaussian chain rule (conic -> cov2D -> cov3D -> scale/rot, mean2D/depth -> mean3D, SH)
+cudaError_t launch_gauss_backward(const GaussBackwardArgs& a, cudaStream_t s);
+
+// debug.cu
+cudaError_t launch_unpack_geom(int P, GeomState geom, float* means2D, float* depths, float* conic_opacity, float* rgb,
+                               float* cov3D, uint32_t* tiles_touched, uint8_t* clamped, cudaStream_t s);
+cudaError_t launch_unpack_bins(int W, int H, ImageState img, const Splat* stream, int64_t capacity,
+                               uint32_t* point_list, uint32_t* ranges, uint32_t* n_contrib, cudaStream_t s);
+
+}  // namespace gdr

@@ -1,0 +1,283 @@
+// Stage 1: per-Gaussian projection + tile counting (one launch).
+//
+// Replaces the reference's preprocessCUDA forward
+// (RAST/cuda_rasterizer/forward.cu:155-256 with computeCov3D :118-152,
+// computeCov2D :74-113, computeColorFromSH :20-71, in_frustum auxiliary.h:139-164,
+// getRect auxiliary.h:46-56) and the tiles_touched half of its binning
+// (rasterizer_impl.cu:278 scan input).  Differences in structure, not in values:
+//   * inputs with a 12-byte stride (means, scales, SH rows) are staged through
+//     shared memory with coalesced 128-bit loads;
+//   * the outputs of the blend are written as one packed 48-byte Splat record;
+//   * the same launch bumps the per-tile bin counters with warp-aggregated
+//     atomics (tile_iter.cuh), so no separate counting pass over the Gaussians
+//     and no per-Gaussian prefix sum is needed.
+#include "kernels.h"
+#include "tile_iter.cuh"
+
+namespace gdr {
+
+namespace {
+
+constexpr int PROJ_THREADS = 128;
+
+__device__ constexpr float kSH0 = 0.28209479177387814f;
+__device__ constexpr float kSH1 = 0.4886025119029199f;
+__device__ constexpr float kSH2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                      -1.0925484305920792f, 0.5462742152960396f};
+__device__ constexpr float kSH3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                      0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                      -0.5900435899266435f};
+
+// Copy `count` floats from g (global) to s (shared) with 128-bit loads when the
+// source is 16-byte aligned, scalar loads otherwise.  All threads of the CTA call.
+__device__ __forceinline__ void stage_floats(float* s, const float* __restrict__ g, int count) {
+    if ((((uintptr_t)g) & 15u) == 0) {
+        const int n4 = count >> 2;
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        float4* s4 = reinterpret_cast<float4*>(s);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) s4[i] = __ldg(g4 + i);
+        for (int i = (n4 << 2) + threadIdx.x; i < count; i += blockDim.x) s[i] = __ldg(g + i);
+    } else {
+        for (int i = threadIdx.x; i < count; i += blockDim.x) s[i] = __ldg(g + i);
+    }
+}
+
+// World covariance from scale + (un-normalised) quaternion: Sigma = (S R)^T (S R).
+__device__ __forceinline__ void cov3d_from_scale_rot(float3 scale, float mod, float4 q, float* cov3D) {
+    Mat3 S;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) S.m[c][r] = (c == r) ? 1.0f : 0.0f;
+    S.m[0][0] = mod * scale.x;
+    S.m[1][1] = mod * scale.y;
+    S.m[2][2] = mod * scale.z;
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    Mat3 R;
+    R.m[0][0] = 1.f - 2.f * (y * y + z * z);
+    R.m[0][1] = 2.f * (x * y - r * z);
+    R.m[0][2] = 2.f * (x * z + r * y);
+    R.m[1][0] = 2.f * (x * y + r * z);
+    R.m[1][1] = 1.f - 2.f * (x * x + z * z);
+    R.m[1][2] = 2.f * (y * z - r * x);
+    R.m[2][0] = 2.f * (x * z - r * y);
+    R.m[2][1] = 2.f * (y * z + r * x);
+    R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+    const Mat3 M = mat3_mul(S, R);
+    const Mat3 Sigma = mat3_mul(mat3_transpose(M), M);
+    cov3D[0] = Sigma.m[0][0];
+    cov3D[1] = Sigma.m[0][1];
+    cov3D[2] = Sigma.m[0][2];
+    cov3D[3] = Sigma.m[1][1];
+    cov3D[4] = Sigma.m[1][2];
+    cov3D[5] = Sigma.m[2][2];
+}
+
+// EWA screen-space covariance (a, b, c) with the 0.3 px low-pass.
+__device__ __forceinline__ float3 cov2d_ewa(const float3 mean, float focal_x, float focal_y, float tan_fovx,
+                                            float tan_fovy, const float* cov3D, const float* __restrict__ view) {
+    float3 t = xform_point_4x3(mean, view);
+    const float limx = 1.3f * tan_fovx;
+    const float limy = 1.3f * tan_fovy;
+    const float txtz = t.x / t.z;
+    const float tytz = t.y / t.z;
+    t.x = min(limx, max(-limx, txtz)) * t.z;
+    t.y = min(limy, max(-limy, tytz)) * t.z;
+
+    Mat3 J;
+    J.m[0][0] = focal_x / t.z;
+    J.m[0][1] = 0.0f;
+    J.m[0][2] = -(focal_x * t.x) / (t.z * t.z);
+    J.m[1][0] = 0.0f;
+    J.m[1][1] = focal_y / t.z;
+    J.m[1][2] = -(focal_y * t.y) / (t.z * t.z);
+    J.m[2][0] = 0.0f;
+    J.m[2][1] = 0.0f;
+    J.m[2][2] = 0.0f;
+    Mat3 Wm;
+    Wm.m[0][0] = view[0]; Wm.m[0][1] = view[4]; Wm.m[0][2] = view[8];
+    Wm.m[1][0] = view[1]; Wm.m[1][1] = view[5]; Wm.m[1][2] = view[9];
+    Wm.m[2][0] = view[2]; Wm.m[2][1] = view[6]; Wm.m[2][2] = view[10];
+    const Mat3 T = mat3_mul(Wm, J);
+    Mat3 Vrk;
+    Vrk.m[0][0] = cov3D[0]; Vrk.m[0][1] = cov3D[1]; Vrk.m[0][2] = cov3D[2];
+    Vrk.m[1][0] = cov3D[1]; Vrk.m[1][1] = cov3D[3]; Vrk.m[1][2] = cov3D[4];
+    Vrk.m[2][0] = cov3D[2]; Vrk.m[2][1] = cov3D[4]; Vrk.m[2][2] = cov3D[5];
+    Mat3 cov = mat3_mul(mat3_mul(mat3_transpose(T), mat3_transpose(Vrk)), T);
+    cov.m[0][0] += 0.3f;
+    cov.m[1][1] += 0.3f;
+    return make_float3(cov.m[0][0], cov.m[0][1], cov.m[1][1]);
+}
+
+// View-dependent colour from SH coefficients sh[k*3 + ch] (k < (deg+1)^2), +0.5, clamped at 0.
+__device__ __forceinline__ float3 sh_to_rgb(int deg, float3 pos, float3 campos, const float* sh, unsigned& clamp_bits) {
+    float3 dir = make_float3(pos.x - campos.x, pos.y - campos.y, pos.z - campos.z);
+    const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+    dir.x = dir.x / len;
+    dir.y = dir.y / len;
+    dir.z = dir.z / len;
+    const float x = dir.x, y = dir.y, z = dir.z;
+    float res[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        float v = kSH0 * sh[ch];
+        if (deg > 0) {
+            v = v - kSH1 * y * sh[3 + ch] + kSH1 * z * sh[6 + ch] - kSH1 * x * sh[9 + ch];
+            if (deg > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z;
+                const float xy = x * y, yz = y * z, xz = x * z;
+                v = v + kSH2[0] * xy * sh[12 + ch] + kSH2[1] * yz * sh[15 + ch] +
+                    kSH2[2] * (2.0f * zz - xx - yy) * sh[18 + ch] + kSH2[3] * xz * sh[21 + ch] +
+                    kSH2[4] * (xx - yy) * sh[24 + ch];
+                if (deg > 2) {
+                    v = v + kSH3[0] * y * (3.0f * xx - yy) * sh[27 + ch] + kSH3[1] * xy * z * sh[30 + ch] +
+                        kSH3[2] * y * (4.0f * zz - xx - yy) * sh[33 + ch] +
+                        kSH3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + ch] +
+                        kSH3[4] * x * (4.0f * zz - xx - yy) * sh[39 + ch] + kSH3[5] * z * (xx - yy) * sh[42 + ch] +
+                        kSH3[6] * x * (xx - 3.0f * yy) * sh[45 + ch];
+                }
+            }
+        }
+        v += 0.5f;
+        if (v < 0) clamp_bits |= (1u << ch);
+        res[ch] = fmaxf(v, 0.0f);
+    }
+    return make_float3(res[0], res[1], res[2]);
+}
+
+__global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int first = blockIdx.x * PROJ_THREADS;
+    const int n_items = min(PROJ_THREADS, a.P - first);
+    const int idx = first + threadIdx.x;
+    const bool in_range = threadIdx.x < n_items;
+
+    // ---- stage the 12-byte-stride inputs with coalesced 128-bit loads ----
+    float* s_mean = smem;                          // 3 * PROJ_THREADS
+    float* s_scale = s_mean + 3 * PROJ_THREADS;    // 3 * PROJ_THREADS
+    float* s_sh = s_scale + 3 * PROJ_THREADS;      // 3 * M * PROJ_THREADS
+    stage_floats(s_mean, a.means3D + (size_t)first * 3, n_items * 3);
+    if (a.cov3D_precomp == nullptr) stage_floats(s_scale, a.scales + (size_t)first * 3, n_items * 3);
+    const bool use_sh = a.colors_precomp == nullptr;
+    if (use_sh) stage_floats(s_sh, a.shs + (size_t)first * 3 * a.M, n_items * 3 * a.M);
+    __syncthreads();
+
+    int n_tiles = 0, rx0 = 0, ry0 = 0, rw = 0;
+    if (in_range) {
+        int radius_out = 0;
+        Splat rec;
+        rec.q0 = make_float4(0.f, 0.f, 0.f, __int_as_float(idx));
+        rec.q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        rec.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned clamp_bits = 0;
+        float cov3D[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+
+        const float3 p_orig = make_float3(s_mean[3 * threadIdx.x], s_mean[3 * threadIdx.x + 1],
+                                          s_mean[3 * threadIdx.x + 2]);
+        const float4 p_hom = xform_point_4x4(p_orig, a.projmatrix);
+        const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+        const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
+        const float3 p_view = xform_point_4x3(p_orig, a.viewmatrix);
+
+        if (p_view.z > NEAR_Z) {  // near-plane cull only (auxiliary.h:152)
+            if (a.cov3D_precomp != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) cov3D[k] = __ldg(a.cov3D_precomp + (size_t)idx * 6 + k);
+            } else {
+                const float3 sc = make_float3(s_scale[3 * threadIdx.x], s_scale[3 * threadIdx.x + 1],
+                                              s_scale[3 * threadIdx.x + 2]);
+                const float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+                cov3d_from_scale_rot(sc, a.scale_modifier, q, cov3D);
+            }
+            const float3 cov = cov2d_ewa(p_orig, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, cov3D, a.viewmatrix);
+            const float det = (cov.x * cov.z - cov.y * cov.y);
+            if (det != 0.0f) {
+                const float det_inv = 1.f / det;
+                const float3 conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
+                const float mid = 0.5f * (cov.x + cov.z);
+                const float lambda1 = mid + sqrtf(max(0.1f, mid * mid - det));
+                const float lambda2 = mid - sqrtf(max(0.1f, mid * mid - det));
+                const float my_radius = ceilf(3.f * sqrtf(max(lambda1, lambda2)));
+                const float2 pix = make_float2(ndc_to_pix(p_proj.x, a.W), ndc_to_pix(p_proj.y, a.H));
+                int x0, y0, x1, y1;
+                tile_rect(pix.x, pix.y, (int)my_radius, a.gx, a.gy, x0, y0, x1, y1);
+                if ((x1 - x0) * (y1 - y0) != 0) {
+                    float3 rgb;
+                    if (use_sh) {
+                        const float3 cam = make_float3(__ldg(a.campos), __ldg(a.campos + 1), __ldg(a.campos + 2));
+                        rgb = sh_to_rgb(a.sh_degree, p_orig, cam, s_sh + (size_t)threadIdx.x * 3 * a.M, clamp_bits);
+                    } else {
+                        rgb = make_float3(__ldg(a.colors_precomp + (size_t)idx * 3),
+                                          __ldg(a.colors_precomp + (size_t)idx * 3 + 1),
+                                          __ldg(a.colors_precomp + (size_t)idx * 3 + 2));
+                    }
+                    const float opacity = __ldg(a.opacities + idx);
+                    // Conservative reject threshold: power < thr  =>  opacity*exp(power) < 1/255 for certain
+                    // (1e-4 of slack in the exponent dwarfs every rounding error of the exact test).
+                    const float thr = opacity > 0.f ? (logf(ALPHA_MIN / opacity) - 1e-4f) : (opacity <= 0.f ? INFINITY : 0.0f);
+                    radius_out = (int)my_radius;
+                    rec.q0 = make_float4(pix.x, pix.y, p_view.z, __int_as_float(idx));
+                    rec.q1 = make_float4(conic.x, conic.y, conic.z, opacity);
+                    rec.q2 = make_float4(rgb.x, rgb.y, rgb.z, thr);
+                    rx0 = x0;
+                    ry0 = y0;
+                    rw = x1 - x0;
+                    n_tiles = (y1 - y0) * (x1 - x0);
+                }
+            }
+        } else if (a.prefiltered) {
+            atomicOr(&a.img.header[HDR_OVERFLOW], 2u);  // reference traps here (auxiliary.h:154-158); we flag
+        }
+        a.radii[idx] = radius_out;
+        a.geom.splat[idx] = rec;
+        a.geom.tiles_touched[idx] = (uint32_t)n_tiles;
+        a.geom.clamped[idx] = (uint8_t)clamp_bits;
+        if (a.cov3D_precomp == nullptr) {
+            float2* c = reinterpret_cast<float2*>(a.geom.cov3D + (size_t)idx * 6);
+            c[0] = make_float2(cov3D[0], cov3D[1]);
+            c[1] = make_float2(cov3D[2], cov3D[3]);
+            c[2] = make_float2(cov3D[4], cov3D[5]);
+        }
+    }
+
+    // ---- bin counters: one aggregated atomic per distinct tile per warp step ----
+    uint32_t* counter = a.img.tile_counter;
+    warp_foreach_tile(n_tiles, rx0, ry0, rw, a.gx, [&](int tile, int, int, bool valid, unsigned active) {
+        if (valid) {
+            const unsigned peers = __match_any_sync(active, tile);
+            if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&counter[tile], (unsigned)__popc(peers));
+        }
+    });
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
+                                    uint8_t* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float3 p = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+    const float3 v = xform_point_4x3(p, view);
+    present[idx] = v.z > NEAR_Z;
+}
+
+}  // namespace
+
+cudaError_t launch_project(const ProjectArgs& a, cudaStream_t s) {
+    if (a.P <= 0) return cudaSuccess;
+    const size_t smem = sizeof(float) * PROJ_THREADS * (6 + 3 * (size_t)(a.colors_precomp ? 0 : a.M));
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int grid = (a.P + PROJ_THREADS - 1) / PROJ_THREADS;
+    project_kernel<<<grid, PROJ_THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
+                                cudaStream_t s) {
+    if (P <= 0) return cudaSuccess;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, viewmatrix, present);
+    return cudaGetLastError();
+}
+
+}  // namespace gdr

@@ -1,0 +1,87 @@
+// Layout of the caller-owned opaque state buffers (see include/gdr.h).
+//
+// GeomState  (reference: GeometryState, rasterizer_impl.h:33-48) -- per Gaussian:
+//     Splat    splat[P]          48 B   packed blend record (xy, depth, id | conic, opacity | rgb, reject threshold)
+//     float    cov3D[6P]         24 B   world covariance (needed by the backward)
+//     uint32   tiles_touched[P]   4 B
+//     uint8    clamped[P]         1 B   bit c set <=> SH colour channel c was clamped at 0
+// ImageState (reference: ImageState, rasterizer_impl.h:50-56) -- per view:
+//     uint32   header[64]               header[0] = R (instances), header[1] = overflow flag
+//     uint32   tile_offsets[T + 1]      exclusive scan of per-tile instance counts (the reference's `ranges`)
+//     uint32   tile_counter[T]          bin counters (count pass, then emit cursors)
+//     uint32   n_contrib[H * W]
+// SplatStream (reference: BinningState.point_list, but materialised):
+//     Splat    stream[capacity]         per-tile, depth-sorted copies of the Gaussians' records,
+//                                       contiguous per tile so a tile is staged with cp.async.bulk
+// SortScratch: uint64 keys[capacity], uint64 keys_alt[capacity]
+#pragma once
+#include "common.cuh"
+
+namespace gdr {
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct GeomState {
+    Splat* splat;
+    float* cov3D;
+    uint32_t* tiles_touched;
+    uint8_t* clamped;
+    static __host__ __device__ size_t bytes(size_t P) {
+        size_t o = 0;
+        o = align_up(o + sizeof(Splat) * P, 256);
+        o = align_up(o + sizeof(float) * 6 * P, 256);
+        o = align_up(o + sizeof(uint32_t) * P, 256);
+        o = align_up(o + P, 256);
+        return o + 256;
+    }
+    static __host__ __device__ GeomState carve(void* base, size_t P) {
+        GeomState g;
+        char* p = (char*)base;
+        size_t o = 0;
+        g.splat = (Splat*)(p + o);
+        o = align_up(o + sizeof(Splat) * P, 256);
+        g.cov3D = (float*)(p + o);
+        o = align_up(o + sizeof(float) * 6 * P, 256);
+        g.tiles_touched = (uint32_t*)(p + o);
+        o = align_up(o + sizeof(uint32_t) * P, 256);
+        g.clamped = (uint8_t*)(p + o);
+        return g;
+    }
+};
+
+constexpr int IMG_HEADER_WORDS = 64;
+constexpr int HDR_NUM_RENDERED = 0;
+constexpr int HDR_OVERFLOW = 1;
+constexpr int HDR_MAX_TILE = 2;
+
+struct ImageState {
+    uint32_t* header;
+    uint32_t* tile_offsets;
+    uint32_t* tile_counter;
+    uint32_t* n_contrib;
+    static __host__ __device__ size_t bytes(int W, int H) {
+        const size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+        size_t o = 0;
+        o = align_up(o + 4 * IMG_HEADER_WORDS, 256);
+        o = align_up(o + 4 * (T + 1), 256);
+        o = align_up(o + 4 * T, 256);
+        o = align_up(o + 4 * (size_t)W * H, 256);
+        return o + 256;
+    }
+    static __host__ __device__ ImageState carve(void* base, int W, int H) {
+        const size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+        ImageState s;
+        char* p = (char*)base;
+        size_t o = 0;
+        s.header = (uint32_t*)(p + o);
+        o = align_up(o + 4 * IMG_HEADER_WORDS, 256);
+        s.tile_offsets = (uint32_t*)(p + o);
+        o = align_up(o + 4 * (T + 1), 256);
+        s.tile_counter = (uint32_t*)(p + o);
+        o = align_up(o + 4 * T, 256);
+        s.n_contrib = (uint32_t*)(p + o);
+        return s;
+    }
+};
+
+}  // namespace gdr

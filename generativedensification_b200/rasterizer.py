@@ -1,0 +1,364 @@
+"""Host-side mirror of the reference's `diff_gaussian_rasterization` Python API.
+
+Same names, argument order, return values and error behaviour as
+RAST/diff_gaussian_rasterization/__init__.py in the reference tree
+(RAST/ = third_party/diff-gaussian-rasterization/):
+
+    GaussianRasterizationSettings   __init__.py:160-172  (NamedTuple, identical fields)
+    GaussianRasterizer              __init__.py:174-223  (nn.Module; forward, markVisible)
+    rasterize_gaussians             __init__.py:21-42
+    _RasterizeGaussians             __init__.py:44-158   (autograd.Function; 9 inputs, 9 grads)
+
+so `lightning/renderer.py` and `lightning/point_decoder/layers/gaussian_renderer.py`
+run unchanged against it.  Everything below the Python surface is libgdr.so (C ABI
+in include/gdr.h): torch is used only to allocate device buffers and to supply the
+current CUDA stream.
+
+Differences from the reference that callers cannot observe through the returned
+tensors:
+  * kernels run on torch's *current* stream (the reference uses the legacy default
+    stream) and the host never drains the GPU: the instance count R is read from
+    pinned memory after an event that fires right after the tile scan, while the
+    rest of the frame is already enqueued with a predicted capacity; only a
+    mis-prediction (first call for a new scene size, or R grew by > 50 %) costs
+    a second `gdr_forward_render`;
+  * `ctx.needs_input_grad` is honoured (the reference computes every gradient
+    every time); incoming `None` grads for depth / alpha are skipped instead of
+    being materialised as zeros.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def cpu_deep_copy_tuple(input_tuple):
+    copied_tensors = [item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple]
+    return tuple(copied_tensors)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+# ------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, device) -> torch.Tensor:
+    """contiguous FP32 on `device` (the reference calls .contiguous() on every input)."""
+    if t.numel() == 0:
+        return t
+    if t.dtype != torch.float32:
+        raise TypeError(f"rasterizer inputs must be float32, got {t.dtype}")
+    if t.device != device:
+        t = t.to(device)
+    return t.contiguous()
+
+
+class _CapacityPredictor:
+    """Remembers the last instance count per (device, P, H, W) to size the next frame's buffers."""
+
+    def __init__(self):
+        self.last = {}
+
+    def predict(self, key) -> int:
+        r = self.last.get(key)
+        return 0 if r is None else int(r * 1.5) + 4096
+
+    def update(self, key, r: int) -> None:
+        self.last[key] = r
+
+
+_predictor = _CapacityPredictor()
+_mailboxes = {}
+
+
+def _mailbox(device) -> torch.Tensor:
+    """Small ring of pinned int32 slots the GPU writes R into."""
+    mb = _mailboxes.get(device)
+    if mb is None:
+        mb = {"buf": torch.zeros(64, dtype=torch.int32).pin_memory(), "next": 0}
+        _mailboxes[device] = mb
+    i = mb["next"]
+    mb["next"] = (i + 1) % 64
+    return mb["buf"][i:i + 1]
+
+
+class _ForwardState:
+    """Opaque state kept between forward and backward (the reference keeps three byte tensors)."""
+    __slots__ = ("geom", "img", "stream_buf", "capacity", "num_rendered", "P", "M")
+
+
+def _forward_impl(settings: GaussianRasterizationSettings, means3D, sh, colors_precomp, opacities, scales, rotations,
+                  cov3Ds_precomp):
+    lib = _lib.load()
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
+    if not means3D.is_cuda:
+        raise RuntimeError("means3D must be a CUDA tensor: this rasterizer has no CPU path")
+    device = means3D.device
+    P = means3D.size(0)
+    H, W = int(settings.image_height), int(settings.image_width)
+    f32 = dict(dtype=torch.float32, device=device)
+
+    st = _ForwardState()
+    st.P = P
+    st.M = sh.size(1) if sh.numel() != 0 else 0
+    st.capacity = 0
+    st.num_rendered = 0
+    st.geom = st.img = st.stream_buf = None
+    radii = torch.empty(P, dtype=torch.int32, device=device)
+    if P == 0:
+        # RasterizeGaussiansCUDA returns its zero-filled images untouched when P == 0 (rasterize_points.cu:83)
+        z = torch.zeros
+        return z(3, H, W, **f32), radii, z(1, H, W, **f32), z(1, H, W, **f32), st
+
+    with torch.cuda.device(device):
+        means3D = _f32c(means3D, device)
+        sh = _f32c(sh, device)
+        colors_precomp = _f32c(colors_precomp, device)
+        opacities = _f32c(opacities, device)
+        scales = _f32c(scales, device)
+        rotations = _f32c(rotations, device)
+        cov3Ds_precomp = _f32c(cov3Ds_precomp, device)
+        bg = _f32c(settings.bg, device)
+        view = _f32c(settings.viewmatrix, device)
+        proj = _f32c(settings.projmatrix, device)
+        campos = _f32c(settings.campos, device)
+        stream = torch.cuda.current_stream(device)
+        sptr = C.c_void_p(stream.cuda_stream)
+
+        st.geom = torch.empty(_lib.query_bytes("gdr_geom_state_bytes", P), dtype=torch.uint8, device=device)
+        st.img = torch.empty(_lib.query_bytes("gdr_image_state_bytes", W, H), dtype=torch.uint8, device=device)
+        mailbox = _mailbox(device)
+        _lib.check(lib.gdr_forward_project(
+            P, int(settings.sh_degree), st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
+            _ptr(scales), float(settings.scale_modifier), _ptr(rotations), _ptr(cov3Ds_precomp), _ptr(view),
+            _ptr(proj), _ptr(campos), float(settings.tanfovx), float(settings.tanfovy), int(bool(settings.prefiltered)),
+            radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(), mailbox.data_ptr(), sptr), "gdr_forward_project")
+        counted = torch.cuda.Event()
+        counted.record(stream)
+
+        color = torch.empty(3, H, W, **f32)
+        depth = torch.empty(1, H, W, **f32)
+        alpha = torch.empty(1, H, W, **f32)
+
+        def render(capacity: int):
+            st.capacity = capacity
+            st.stream_buf = torch.empty(_lib.query_bytes("gdr_splat_stream_bytes", capacity), dtype=torch.uint8,
+                                        device=device)
+            scratch = torch.empty(_lib.query_bytes("gdr_sort_scratch_bytes", capacity), dtype=torch.uint8,
+                                  device=device)
+            _lib.check(lib.gdr_forward_render(
+                P, W, H, _ptr(bg), radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(), st.stream_buf.data_ptr(),
+                scratch.data_ptr(), capacity, color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), sptr),
+                "gdr_forward_render")
+
+        key = (device.index, P, H, W)
+        guess = _predictor.predict(key)
+        if guess > 0:
+            render(guess)  # speculative: the GPU keeps working while the host waits for R
+        counted.synchronize()  # waits for project + tile scan only, not for the frame
+        R = int(mailbox.item())
+        _predictor.update(key, R)
+        st.num_rendered = R
+        if guess == 0 or R > guess:
+            render(R)
+        if settings.prefiltered:
+            pass  # the reference traps on-device if a prefiltered point is culled; we do not abort the context
+    return color, radii, depth, alpha, st
+
+
+def _backward_impl(settings, st: _ForwardState, saved, grad_color, grad_depth, grad_alpha, needs):
+    """needs = (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)."""
+    lib = _lib.load()
+    colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, alpha = saved
+    device = means3D.device
+    colors_precomp, means3D, scales, rotations, cov3Ds_precomp, sh = (
+        _f32c(t, device) for t in (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, sh))
+    P, M = st.P, st.M
+    H, W = int(settings.image_height), int(settings.image_width)
+    f32 = dict(dtype=torch.float32, device=device)
+    need_m3, need_m2, need_sh, need_col, need_op, need_sc, need_rot, need_cov = needs
+    out = dict(means2D=None, colors=None, opacity=None, means3D=None, cov3D=None, sh=None, scales=None, rot=None)
+    if P == 0:
+        z = torch.zeros
+        return dict(means2D=z(0, 4, **f32), colors=z(0, 3, **f32), opacity=z(0, 1, **f32), means3D=z(0, 3, **f32),
+                    cov3D=z(0, 6, **f32), sh=z(0, M, 3, **f32), scales=z(0, 3, **f32), rot=z(0, 4, **f32))
+    mask = 0
+    if need_m2:
+        mask |= _lib.GRAD_MEANS2D
+        out["means2D"] = torch.empty(P, 4, **f32)
+    if need_m3:
+        mask |= _lib.GRAD_MEANS3D
+        out["means3D"] = torch.empty(P, 3, **f32)
+    if need_sh and sh.numel():
+        mask |= _lib.GRAD_COLOR
+        out["sh"] = torch.empty(P, M, 3, **f32)
+    if need_col and colors_precomp.numel():
+        mask |= _lib.GRAD_COLOR
+        out["colors"] = torch.empty(P, 3, **f32)
+    if need_op:
+        mask |= _lib.GRAD_OPACITY
+        out["opacity"] = torch.empty(P, 1, **f32)
+    if (need_sc or need_rot) and scales.numel():
+        mask |= _lib.GRAD_COV
+        out["scales"] = torch.empty(P, 3, **f32)
+        out["rot"] = torch.empty(P, 4, **f32)
+    if need_cov and cov3Ds_precomp.numel():
+        mask |= _lib.GRAD_COV
+        out["cov3D"] = torch.empty(P, 6, **f32)
+    if mask == 0:
+        return out
+    with torch.cuda.device(device):
+        bg = _f32c(settings.bg, device)
+        view = _f32c(settings.viewmatrix, device)
+        proj = _f32c(settings.projmatrix, device)
+        campos = _f32c(settings.campos, device)
+        grad_color = _f32c(grad_color, device)
+        grad_depth = None if grad_depth is None else _f32c(grad_depth, device)
+        grad_alpha = None if grad_alpha is None else _f32c(grad_alpha, device)
+        scratch = torch.empty(_lib.query_bytes("gdr_backward_scratch_bytes", P), dtype=torch.uint8, device=device)
+        sptr = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(lib.gdr_backward(
+            P, int(settings.sh_degree), M, W, H, _ptr(bg), _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(scales),
+            float(settings.scale_modifier), _ptr(rotations), _ptr(cov3Ds_precomp), _ptr(view), _ptr(proj), _ptr(campos),
+            float(settings.tanfovx), float(settings.tanfovy), radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(),
+            _ptr(st.stream_buf), st.capacity, alpha.data_ptr(), grad_color.data_ptr(), _ptr(grad_depth),
+            _ptr(grad_alpha), scratch.data_ptr(), mask, _ptr(out["means2D"]), _ptr(out["colors"]),
+            _ptr(out["opacity"]), _ptr(out["means3D"]), _ptr(out["cov3D"]), _ptr(out["sh"]), _ptr(out["scales"]),
+            _ptr(out["rot"]), sptr), "gdr_backward")
+    return out
+
+
+# ------------------------------------------------------------------------------
+# public API (mirrors the reference)
+# ------------------------------------------------------------------------------
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        args = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
+        if raster_settings.debug:
+            cpu_args = cpu_deep_copy_tuple((raster_settings.bg, *args, raster_settings.viewmatrix,
+                                            raster_settings.projmatrix, raster_settings.campos))
+            try:
+                color, radii, depth, alpha, st = _forward_impl(raster_settings, *args)
+                torch.cuda.synchronize(means3D.device)  # debug mode surfaces CUDA errors here (auxiliary.h:166-173)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            color, radii, depth, alpha, st = _forward_impl(raster_settings, *args)
+
+        ctx.raster_settings = raster_settings
+        ctx.num_rendered = st.num_rendered
+        ctx.state = st
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, alpha)
+        ctx.mark_non_differentiable(radii)
+        ctx.set_materialize_grads(False)
+        return color, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
+        raster_settings = ctx.raster_settings
+        st = ctx.state
+        saved = ctx.saved_tensors
+        means3D = saved[1]
+        H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+        if grad_color is None:
+            grad_color = torch.zeros(3, H, W, dtype=torch.float32, device=means3D.device)
+        needs = tuple(ctx.needs_input_grad[:8])
+        if raster_settings.debug:
+            cpu_args = cpu_deep_copy_tuple((raster_settings.bg, *saved, grad_color, grad_depth, grad_alpha))
+            try:
+                g = _backward_impl(raster_settings, st, saved, grad_color, grad_depth, grad_alpha, needs)
+                torch.cuda.synchronize(means3D.device)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise ex
+        else:
+            g = _backward_impl(raster_settings, st, saved, grad_color, grad_depth, grad_alpha, needs)
+        # same order as the reference (__init__.py:146-156)
+        return (g["means3D"], g["means2D"], g["sh"], g["colors"], g["opacity"], g["scales"], g["rot"], g["cov3D"],
+                None)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        # Mark visible points (based on frustum culling for camera) with a boolean
+        with torch.no_grad():
+            rs = self.raster_settings
+            lib = _lib.load()
+            positions = _f32c(positions, positions.device)
+            if not positions.is_cuda:
+                raise RuntimeError("positions must be a CUDA tensor")
+            P = positions.size(0)
+            visible = torch.zeros(P, dtype=torch.bool, device=positions.device)
+            if P:
+                with torch.cuda.device(positions.device):
+                    view = _f32c(rs.viewmatrix, positions.device)
+                    proj = _f32c(rs.projmatrix, positions.device)
+                    sptr = C.c_void_p(torch.cuda.current_stream(positions.device).cuda_stream)
+                    _lib.check(lib.gdr_mark_visible(P, positions.data_ptr(), view.data_ptr(), proj.data_ptr(),
+                                                    visible.data_ptr(), sptr), "gdr_mark_visible")
+        return visible
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        raster_settings = self.raster_settings
+
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                   raster_settings)

@@ -1,0 +1,136 @@
+/*
+ * gdr.h -- C ABI of the B200-native Gaussian rasterizer (libgdr.so).
+ *
+ * This is the drop-in boundary for the reference's native rasterizer module
+ * `diff_gaussian_rasterization._C` (reference tree, RAST/ =
+ * third_party/diff-gaussian-rasterization/):
+ *
+ *   reference entry point (RAST/ext.cpp:15-19)                    replaced by
+ *   ----------------------------------------------------------    ---------------------------------
+ *   rasterize_gaussians  = RasterizeGaussiansCUDA                  gdr_forward_project + gdr_forward_render
+ *       (RAST/rasterize_points.h:18-38, rasterize_points.cu:35-119;
+ *        Rasterizer::forward RAST/cuda_rasterizer/rasterizer_impl.cu:197-339)
+ *   rasterize_gaussians_backward = RasterizeGaussiansBackwardCUDA  gdr_backward
+ *       (RAST/rasterize_points.h:40-65, rasterize_points.cu:121-208;
+ *        Rasterizer::backward rasterizer_impl.cu:343-447)
+ *   mark_visible = markVisible                                     gdr_mark_visible
+ *       (RAST/rasterize_points.h:67-70, rasterize_points.cu:210-229)
+ *   the three resizable byte buffers geomBuffer / binningBuffer /  gdr_*_bytes size queries; the caller
+ *   imgBuffer (rasterize_points.cu:27-33,75-80;                    allocates and owns every buffer
+ *   rasterizer_impl.h:22-73)
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer to contiguous FP32/INT32 data unless the
+ *     parameter name ends in `_host`.  A null pointer means "not provided"
+ *     exactly as an empty tensor does in the reference (colors_precomp == NULL
+ *     -> colours from SH; cov3D_precomp == NULL -> covariance from
+ *     scales/rotations).
+ *   - viewmatrix / projmatrix are the reference's transposed (row-vector) 4x4
+ *     matrices, 16 floats each, on the device; campos and bg are 3 device floats.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*).  No
+ *     entry point synchronises the device or the stream.
+ *   - Return value: GDR_OK (0) or a negative error code; gdr_last_error() returns
+ *     a thread-local message.  Nothing throws across the ABI.
+ *   - The library keeps no state between calls; all buffers (including the state
+ *     saved between forward and backward) are caller-owned.
+ *
+ * The forward is split in two so that the host never has to drain the GPU to
+ * learn the instance count R (the reference blocks on a cudaMemcpy of it,
+ * rasterizer_impl.cu:282):
+ *   1. gdr_forward_project  -- per-Gaussian projection, tile counting, tile scan;
+ *      enqueues an async copy of R into `num_rendered_host` (pinned memory).
+ *   2. gdr_forward_render   -- instance emission, per-tile depth sort, blend; runs
+ *      with a caller-chosen instance capacity.  If R turns out to exceed the
+ *      capacity the kernels stay in bounds and the caller re-runs step 2 with a
+ *      larger buffer (the Python shim does this speculatively).
+ */
+#ifndef GDR_H_INCLUDED
+#define GDR_H_INCLUDED
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GDR_API __attribute__((visibility("default")))
+#else
+#define GDR_API
+#endif
+
+#define GDR_OK 0
+#define GDR_ERR_INVALID_ARGUMENT (-1)
+#define GDR_ERR_CUDA (-2)
+#define GDR_ERR_UNSUPPORTED (-3)
+
+#define GDR_ABI_VERSION 1
+
+/* bit flags for gdr_backward(grad_mask): which input gradients the caller needs */
+#define GDR_GRAD_MEANS2D 1
+#define GDR_GRAD_MEANS3D 2
+#define GDR_GRAD_COLOR 4   /* dL/dsh or dL/dcolors_precomp */
+#define GDR_GRAD_OPACITY 8
+#define GDR_GRAD_COV 16    /* dL/dscales + dL/drotations, or dL/dcov3D_precomp */
+#define GDR_GRAD_ALL 31
+
+GDR_API int gdr_abi_version(void);
+GDR_API const char* gdr_last_error(void);
+
+/* Size queries for the caller-owned opaque buffers (all 256-byte aligned device memory). */
+GDR_API int gdr_geom_state_bytes(int P, int64_t* bytes);              /* per-Gaussian state (reference: GeometryState) */
+GDR_API int gdr_image_state_bytes(int W, int H, int64_t* bytes);      /* per-pixel/per-tile state (reference: ImageState) */
+GDR_API int gdr_splat_stream_bytes(int64_t capacity, int64_t* bytes); /* depth-sorted per-tile instance stream, saved for backward */
+GDR_API int gdr_sort_scratch_bytes(int64_t capacity, int64_t* bytes); /* temporary, free after gdr_forward_render */
+GDR_API int gdr_backward_scratch_bytes(int P, int64_t* bytes);        /* temporary screen-space gradient accumulators */
+
+/* Step 1 of the forward (replaces the first half of Rasterizer::forward, rasterizer_impl.cu:197-282). */
+GDR_API int gdr_forward_project(int P, int sh_degree, int M, int W, int H,
+                        const float* means3D, const float* shs, const float* colors_precomp,
+                        const float* opacities, const float* scales, float scale_modifier,
+                        const float* rotations, const float* cov3D_precomp,
+                        const float* viewmatrix, const float* projmatrix, const float* campos,
+                        float tan_fovx, float tan_fovy, int prefiltered,
+                        int32_t* radii /* out [P] */, void* geom_state, void* image_state,
+                        int32_t* num_rendered_host /* pinned host memory or NULL */, void* stream);
+
+/* Step 2 of the forward (replaces rasterizer_impl.cu:284-337). out_* are [3,H,W], [1,H,W], [1,H,W]. */
+GDR_API int gdr_forward_render(int P, int W, int H, const float* bg, const int32_t* radii,
+                       const void* geom_state, void* image_state,
+                       void* splat_stream, void* sort_scratch, int64_t capacity,
+                       float* out_color, float* out_depth, float* out_alpha, void* stream);
+
+/* Backward (replaces Rasterizer::backward, rasterizer_impl.cu:343-447).  dL_dout_depth / dL_dout_alpha
+ * may be NULL (treated as zero).  Output gradient pointers may be NULL when the matching bit of
+ * grad_mask is clear; requested outputs are fully written (zeros for culled Gaussians), no pre-zeroing
+ * needed.  dL_dmeans2D is [P,4] = (d/dx_ndc, d/dy_ndc, sum|.|, sum|.|) as in backward.cu:589-594. */
+GDR_API int gdr_backward(int P, int sh_degree, int M, int W, int H, const float* bg,
+                 const float* means3D, const float* shs, const float* colors_precomp,
+                 const float* scales, float scale_modifier, const float* rotations,
+                 const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                 const float* campos, float tan_fovx, float tan_fovy, const int32_t* radii,
+                 const void* geom_state, const void* image_state, const void* splat_stream,
+                 int64_t capacity, const float* out_alpha,
+                 const float* dL_dout_color, const float* dL_dout_depth, const float* dL_dout_alpha,
+                 void* backward_scratch, int grad_mask,
+                 float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
+                 float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drotations, void* stream);
+
+/* present[i] = view-space z > 0.2 (rasterizer_impl.cu:54-66). present is P bytes (bool). */
+GDR_API int gdr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream);
+
+/* Introspection for tests: copies of the per-Gaussian state in the reference's field layout
+ * (geomState.means2D / depths / conic_opacity / rgb / tiles_touched / clamped, rasterizer_impl.h:33-48).
+ * Any output pointer may be NULL. */
+GDR_API int gdr_debug_unpack_geom(int P, const void* geom_state, float* means2D /*[P,2]*/, float* depths /*[P]*/,
+                          float* conic_opacity /*[P,4]*/, float* rgb /*[P,3]*/, float* cov3D /*[P,6]*/,
+                          uint32_t* tiles_touched /*[P]*/, uint8_t* clamped /*[P,3]*/, void* stream);
+/* Sorted Gaussian ids per tile instance ([capacity] uint32) and tile ranges ([tiles,2] uint32). */
+GDR_API int gdr_debug_unpack_bins(int W, int H, const void* image_state, const void* splat_stream, int64_t capacity,
+                          uint32_t* point_list, uint32_t* ranges, uint32_t* n_contrib /*[H,W]*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDR_H_INCLUDED */
