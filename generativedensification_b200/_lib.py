@@ -37,7 +37,23 @@ SIGNATURES = {
     "gdr_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "gdr_debug_unpack_geom": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gdr_debug_unpack_bins": (_i, [_i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "gdr_profile_enable": (_i, [_i]),
+    "gdr_profile_read": (_i, [C.POINTER(C.c_double), _pi64]),
 }
+
+STAGES = ("project", "tile_scan", "emit", "tile_sort", "blend_fwd", "blend_bwd", "gauss_bwd")
+
+
+def profile_enable(on: bool) -> None:
+    check(load().gdr_profile_enable(int(on)), "gdr_profile_enable")
+
+
+def profile_read():
+    """{stage: (total_ms, launches)} since the last read; synchronises on the recorded events."""
+    ms = (C.c_double * len(STAGES))()
+    n = (C.c_int64 * len(STAGES))()
+    check(load().gdr_profile_read(ms, n), "gdr_profile_read")
+    return {s: (float(ms[i]), int(n[i])) for i, s in enumerate(STAGES)}
 
 _lib = None
 

@@ -4,6 +4,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/gdr.h"
 #include "kernels.h"
 
@@ -26,6 +28,33 @@ int cuda_fail(cudaError_t e, const char* where) {
         cudaError_t _e = (call);                     \
         if (_e != cudaSuccess) return cuda_fail(_e, where); \
     } while (0)
+
+// ---- opt-in stage profiler (benchmarks only) ----
+struct StageRecord {
+    int stage;
+    cudaEvent_t start, stop;
+};
+bool g_profile = false;
+std::vector<StageRecord> g_records;
+
+struct StageTimer {
+    cudaStream_t s;
+    int stage;
+    cudaEvent_t start = nullptr, stop = nullptr;
+    StageTimer(int stage_, cudaStream_t s_) : s(s_), stage(stage_) {
+        if (g_profile) {
+            cudaEventCreate(&start);
+            cudaEventCreate(&stop);
+            cudaEventRecord(start, s);
+        }
+    }
+    ~StageTimer() {
+        if (start) {
+            cudaEventRecord(stop, s);
+            g_records.push_back({stage, start, stop});
+        }
+    }
+};
 
 inline int tiles_of(int W, int H) { return ((W + gdr::TILE - 1) / gdr::TILE) * ((H + gdr::TILE - 1) / gdr::TILE); }
 
@@ -109,9 +138,15 @@ int gdr_forward_project(int P, int sh_degree, int M, int W, int H, const float* 
         a.radii = radii;
         a.geom = gdr::GeomState::carve(geom_state, (size_t)P);
         a.img = img;
-        GDR_CUDA(gdr::launch_project(a, s), "project");
+        {
+            StageTimer t(GDR_STAGE_PROJECT, s);
+            GDR_CUDA(gdr::launch_project(a, s), "project");
+        }
     }
-    GDR_CUDA(gdr::launch_tile_scan(T, img, s), "tile_scan");
+    {
+        StageTimer t(GDR_STAGE_TILE_SCAN, s);
+        GDR_CUDA(gdr::launch_tile_scan(T, img, s), "tile_scan");
+    }
     if (num_rendered_host)
         GDR_CUDA(cudaMemcpyAsync(num_rendered_host, img.header + gdr::HDR_NUM_RENDERED, sizeof(int32_t),
                                  cudaMemcpyDeviceToHost, s),
@@ -137,11 +172,21 @@ int gdr_forward_render(int P, int W, int H, const float* bg, const int32_t* radi
         uint64_t* keys = (uint64_t*)sort_scratch;
         uint64_t* keys_alt = (uint64_t*)((char*)sort_scratch + gdr::align_up(sizeof(uint64_t) * (size_t)capacity, 256));
         // the emit cursors are zero here: tile_scan zeroes them and tile_sort re-zeroes them after use
-        GDR_CUDA(gdr::launch_emit(P, W, H, radii, geom, img, keys, capacity, s), "emit");
-        GDR_CUDA(gdr::launch_tile_sort(W, H, geom, img, keys, keys_alt, strm, capacity, s), "tile_sort");
+        {
+            StageTimer t(GDR_STAGE_EMIT, s);
+            GDR_CUDA(gdr::launch_emit(P, W, H, radii, geom, img, keys, capacity, s), "emit");
+        }
+        {
+            StageTimer t(GDR_STAGE_TILE_SORT, s);
+            GDR_CUDA(gdr::launch_tile_sort(W, H, geom, img, keys, keys_alt, strm, capacity, s), "tile_sort");
+        }
     }
-    GDR_CUDA(gdr::launch_blend_forward(W, H, bg, img, strm, (P > 0) ? capacity : 0, out_color, out_depth, out_alpha, s),
-             "blend_forward");
+    {
+        StageTimer t(GDR_STAGE_BLEND_FWD, s);
+        GDR_CUDA(gdr::launch_blend_forward(W, H, bg, img, strm, (P > 0) ? capacity : 0, out_color, out_depth, out_alpha,
+                                           s),
+                 "blend_forward");
+    }
     return GDR_OK;
 }
 
@@ -168,9 +213,12 @@ int gdr_backward(int P, int sh_degree, int M, int W, int H, const float* bg, con
     gdr::GeomState geom = gdr::GeomState::carve(const_cast<void*>(geom_state), (size_t)P);
     float* accum = (float*)backward_scratch;
     GDR_CUDA(cudaMemsetAsync(accum, 0, sizeof(float) * 12 * (size_t)P, s), "memset(accum)");
-    GDR_CUDA(gdr::launch_blend_backward(W, H, bg, img, (const gdr::Splat*)splat_stream, capacity, out_alpha,
-                                        dL_dout_color, dL_dout_depth, dL_dout_alpha, accum, grad_mask, s),
-             "blend_backward");
+    {
+        StageTimer t(GDR_STAGE_BLEND_BWD, s);
+        GDR_CUDA(gdr::launch_blend_backward(W, H, bg, img, (const gdr::Splat*)splat_stream, capacity, out_alpha,
+                                            dL_dout_color, dL_dout_depth, dL_dout_alpha, accum, grad_mask, s),
+                 "blend_backward");
+    }
     gdr::GaussBackwardArgs a;
     a.P = P; a.sh_degree = sh_degree; a.M = M; a.W = W; a.H = H;
     a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.scales = scales;
@@ -184,7 +232,10 @@ int gdr_backward(int P, int sh_degree, int M, int W, int H, const float* bg, con
     a.dL_dmeans3D = dL_dmeans3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh; a.dL_dscales = dL_dscales;
     a.dL_drotations = dL_drotations;
     if (shs && !campos) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_backward: campos is NULL");
-    GDR_CUDA(gdr::launch_gauss_backward(a, s), "gauss_backward");
+    {
+        StageTimer t(GDR_STAGE_GAUSS_BWD, s);
+        GDR_CUDA(gdr::launch_gauss_backward(a, s), "gauss_backward");
+    }
     return GDR_OK;
 }
 
@@ -216,6 +267,28 @@ int gdr_debug_unpack_bins(int W, int H, const void* image_state, const void* spl
     GDR_CUDA(gdr::launch_unpack_bins(W, H, img, (const gdr::Splat*)splat_stream, capacity, point_list, ranges,
                                      n_contrib, (cudaStream_t)stream),
              "unpack_bins");
+    return GDR_OK;
+}
+
+int gdr_profile_enable(int on) {
+    g_profile = on != 0;
+    return GDR_OK;
+}
+
+int gdr_profile_read(double* stage_ms, int64_t* stage_launches) {
+    if (!stage_ms || !stage_launches) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_profile_read: NULL output");
+    for (auto& r : g_records) {
+        GDR_CUDA(cudaEventSynchronize(r.stop), "profile sync");
+        float ms = 0.f;
+        GDR_CUDA(cudaEventElapsedTime(&ms, r.start, r.stop), "profile elapsed");
+        if (r.stage >= 0 && r.stage < GDR_NUM_STAGES) {
+            stage_ms[r.stage] += ms;
+            stage_launches[r.stage] += 1;
+        }
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    g_records.clear();
     return GDR_OK;
 }
 

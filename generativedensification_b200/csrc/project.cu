@@ -43,34 +43,40 @@ __device__ __forceinline__ void stage_floats(float* s, const float* __restrict__
 }
 
 // World covariance from scale + (un-normalised) quaternion: Sigma = (S R)^T (S R).
+// The roundings are pinned with explicit intrinsics: which product of x*z +- r*y etc. gets fused
+// into an FMA decides the last bit of the conic, and through it whether a pair sits above or
+// below the alpha = 1/255 cut.  The sequence below is the one nvcc emits for the reference's
+// computeCov3D (checked against the SASS of the reference build and bit-for-bit on the GPU).
 __device__ __forceinline__ void cov3d_from_scale_rot(float3 scale, float mod, float4 q, float* cov3D) {
-    Mat3 S;
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    const float xz = __fmul_rn(x, z), rx = __fmul_rn(r, x), rz = __fmul_rn(r, z);
+    const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+    float R[3][3];  // R[c][k]: column c, row k of the reference's rotation matrix
+    R[0][0] = __fsub_rn(1.f, __fmul_rn(2.f, __fadd_rn(yy, zz)));
+    R[0][1] = __fmul_rn(2.f, __fmaf_rn(x, y, -rz));
+    R[0][2] = __fmul_rn(2.f, __fmaf_rn(r, y, xz));
+    R[1][0] = __fmul_rn(2.f, __fmaf_rn(x, y, rz));
+    R[1][1] = __fsub_rn(1.f, __fmul_rn(2.f, __fmaf_rn(x, x, zz)));
+    R[1][2] = __fmul_rn(2.f, __fmaf_rn(y, z, -rx));
+    R[2][0] = __fmul_rn(2.f, __fmaf_rn(-r, y, xz));
+    R[2][1] = __fmul_rn(2.f, __fmaf_rn(y, z, rx));
+    R[2][2] = __fsub_rn(1.f, __fmul_rn(2.f, __fmaf_rn(x, x, yy)));
+    const float s[3] = {__fmul_rn(mod, scale.x), __fmul_rn(mod, scale.y), __fmul_rn(mod, scale.z)};
+    float M[3][3];  // M = S * R : M[c][k] = s_k * R[c][k]
 #pragma unroll
     for (int c = 0; c < 3; c++)
 #pragma unroll
-        for (int r = 0; r < 3; r++) S.m[c][r] = (c == r) ? 1.0f : 0.0f;
-    S.m[0][0] = mod * scale.x;
-    S.m[1][1] = mod * scale.y;
-    S.m[2][2] = mod * scale.z;
-    const float r = q.x, x = q.y, y = q.z, z = q.w;
-    Mat3 R;
-    R.m[0][0] = 1.f - 2.f * (y * y + z * z);
-    R.m[0][1] = 2.f * (x * y - r * z);
-    R.m[0][2] = 2.f * (x * z + r * y);
-    R.m[1][0] = 2.f * (x * y + r * z);
-    R.m[1][1] = 1.f - 2.f * (x * x + z * z);
-    R.m[1][2] = 2.f * (y * z - r * x);
-    R.m[2][0] = 2.f * (x * z - r * y);
-    R.m[2][1] = 2.f * (y * z + r * x);
-    R.m[2][2] = 1.f - 2.f * (x * x + y * y);
-    const Mat3 M = mat3_mul(S, R);
-    const Mat3 Sigma = mat3_mul(mat3_transpose(M), M);
-    cov3D[0] = Sigma.m[0][0];
-    cov3D[1] = Sigma.m[0][1];
-    cov3D[2] = Sigma.m[0][2];
-    cov3D[3] = Sigma.m[1][1];
-    cov3D[4] = Sigma.m[1][2];
-    cov3D[5] = Sigma.m[2][2];
+        for (int k = 0; k < 3; k++) M[c][k] = __fmul_rn(s[k], R[c][k]);
+    // Sigma[c][r] = sum_k M[r][k] * M[c][k]
+    auto dot3 = [&](int rr, int cc) {
+        return __fmaf_rn(M[rr][2], M[cc][2], __fmaf_rn(M[rr][0], M[cc][0], __fmul_rn(M[rr][1], M[cc][1])));
+    };
+    cov3D[0] = dot3(0, 0);
+    cov3D[1] = dot3(1, 0);
+    cov3D[2] = dot3(2, 0);
+    cov3D[3] = dot3(1, 1);
+    cov3D[4] = dot3(2, 1);
+    cov3D[5] = dot3(2, 2);
 }
 
 // EWA screen-space covariance (a, b, c) with the 0.3 px low-pass.

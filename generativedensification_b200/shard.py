@@ -1,0 +1,96 @@
+"""Sharding of the per-object / per-view render loops over ranks (one process per GPU).
+
+The reference renders every (object, view) pair in nested Python loops on one GPU
+(lightning/network.py:813, 827-838, 848-856, 964-972; eval_all.py:3,9 pins
+CUDA_VISIBLE_DEVICES=0).  Every render is independent given the object's Gaussians, so the
+path shards with NO data-path collective:
+
+  * batch sharding (primary):  objects round-robin over ranks; a rank holds only its objects.
+  * view sharding (one huge object): Gaussians replicated, views strided `rank::world`.
+
+NCCL (torch.distributed) is used only to gather scalars (loss, PSNR, timings) and, in the one
+case where the views of a single object's densify vjp are split across ranks, to sum the
+[P, 4] screen-space gradient (columns 2:4 are sums of absolute values, so they add too).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_items: int, rank: int, world_size: int) -> List[int]:
+    """Strided assignment: item i goes to rank i % world_size (mirrors a round-robin over the loop index)."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    return list(range(rank, n_items, world_size))
+
+
+def init_distributed(backend: str | None = None):
+    """Initialise torch.distributed from the torchrun environment. Returns (rank, world_size, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local_rank
+
+
+def world() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def barrier() -> None:
+    if world() > 1:
+        dist.barrier()
+
+
+def gather_scalars(values: Sequence[float], device) -> torch.Tensor:
+    """All-gather a short vector of fp32 scalars; returns [world, len(values)] on every rank."""
+    t = torch.tensor(list(values), dtype=torch.float32, device=device).reshape(1, -1)
+    if world() == 1:
+        return t
+    out = [torch.empty_like(t) for _ in range(world())]
+    dist.all_gather(out, t)
+    return torch.cat(out, dim=0)
+
+
+def max_over_ranks(x: float, device) -> float:
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    if world() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(t: torch.Tensor) -> torch.Tensor:
+    """In-place sum all-reduce (used for the [P, 4] screen-space gradient when views are split)."""
+    if world() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def gather_view_results(local: Dict[int, torch.Tensor], n_views: int, device) -> List[torch.Tensor]:
+    """Collect per-view scalar results (e.g. PSNR) rendered under view sharding back in view order."""
+    vals = torch.full((n_views,), float("nan"), dtype=torch.float32, device=device)
+    for i, v in local.items():
+        vals[i] = float(v)
+    if world() > 1:
+        gathered = [torch.empty_like(vals) for _ in range(world())]
+        dist.all_gather(gathered, vals)
+        stacked = torch.stack(gathered)
+        vals = torch.nan_to_num(stacked, nan=0.0).sum(0)
+        seen = (~torch.isnan(stacked)).sum(0)
+        if int(seen.min()) != 1 or int(seen.max()) != 1:
+            raise RuntimeError("view sharding did not cover every view exactly once")
+    return vals

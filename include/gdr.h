@@ -130,6 +130,21 @@ GDR_API int gdr_debug_unpack_geom(int P, const void* geom_state, float* means2D 
 GDR_API int gdr_debug_unpack_bins(int W, int H, const void* image_state, const void* splat_stream, int64_t capacity,
                           uint32_t* point_list, uint32_t* ranges, uint32_t* n_contrib /*[H,W]*/, void* stream);
 
+/* Opt-in per-stage device timing for benchmarks (not used on the product path).  While enabled, every
+ * kernel launch is bracketed by cudaEvents on the launch stream.  gdr_profile_read synchronises on the
+ * recorded events, adds the elapsed milliseconds and launch counts per stage into the two arrays
+ * (GDR_NUM_STAGES entries each) and clears the log.  Process-wide and not thread-safe. */
+#define GDR_STAGE_PROJECT 0
+#define GDR_STAGE_TILE_SCAN 1
+#define GDR_STAGE_EMIT 2
+#define GDR_STAGE_TILE_SORT 3
+#define GDR_STAGE_BLEND_FWD 4
+#define GDR_STAGE_BLEND_BWD 5
+#define GDR_STAGE_GAUSS_BWD 6
+#define GDR_NUM_STAGES 7
+GDR_API int gdr_profile_enable(int on);
+GDR_API int gdr_profile_read(double* stage_ms, int64_t* stage_launches);
+
 #ifdef __cplusplus
 }
 #endif

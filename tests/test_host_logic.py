@@ -1,0 +1,99 @@
+"""CPU: host-side logic -- capacity prediction, sharding (world_size 2 over gloo), densify select, synthetic data."""
+import math
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from generativedensification_b200 import densify, shard, synthetic
+from generativedensification_b200.rasterizer import _CapacityPredictor
+
+
+def test_capacity_predictor():
+    p = _CapacityPredictor()
+    assert p.predict(("k",)) == 0          # cold: wait for the real count
+    p.update(("k",), 1000)
+    assert p.predict(("k",)) >= 1500       # 50 % head-room
+    p.update(("k",), 10)
+    assert p.predict(("k",)) >= 15
+
+
+def test_shard_indices_cover_everything_once():
+    for n in (0, 1, 7, 32):
+        for w in (1, 2, 3, 8):
+            seen = sorted(i for r in range(w) for i in shard.shard_indices(n, r, w))
+            assert seen == list(range(n))
+    with pytest.raises(ValueError):
+        shard.shard_indices(4, 2, 2)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w, _ = shard.init_distributed(backend="gloo")
+    dev = torch.device("cpu")
+    mine = shard.shard_indices(8, r, w)
+    # each rank "renders" its views; the per-view scalar is just a function of the view index
+    local = {i: torch.tensor(float(i * i)) for i in mine}
+    vals = shard.gather_view_results(local, 8, dev)
+    g = shard.gather_scalars([float(r), float(len(mine))], dev)
+    grad = torch.full((5, 4), float(r + 1))
+    shard.sum_over_ranks(grad)
+    t = shard.max_over_ranks(10.0 + r, dev)
+    shard.barrier()
+    if r == 0:
+        q.put((vals.tolist(), g.tolist(), grad[0].tolist(), t))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29611 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    vals, g, grad0, t = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert vals == [float(i * i) for i in range(8)]
+    assert g == [[0.0, 4.0], [1.0, 4.0]]
+    assert grad0 == [3.0, 3.0, 3.0, 3.0]       # 1 + 2: the [P,4] gradient sums across ranks
+    assert t == 11.0
+
+
+def test_select_top_k_matches_reference_rule():
+    g = torch.zeros(10, 4)
+    g[:, 2] = torch.arange(10, dtype=torch.float32)
+    g[:, 0] = 100.0  # the signed columns must not matter
+    sel = densify.select_top_k(g, 3)
+    assert sel.tolist() == [False] * 7 + [True] * 3
+    assert densify.select_top_k(g, 20).all()  # fewer points than k: keep all (network.py:886-887)
+    mask = torch.tensor([True] * 5 + [False] * 5)
+    assert densify.select_top_k(g, 2, mask).tolist() == [False, False, False, True, True]
+
+
+def test_synthetic_scene_statistics_and_camera_convention():
+    g = synthetic.make_gaussians(20000, 1234)
+    assert g["means3D"].abs().max() <= 0.5
+    assert abs(g["scales"].log().mean().item() - math.log(0.5 * (2 / 64) / 3)) < 0.01
+    assert torch.allclose(g["rotations"].norm(dim=-1), torch.ones(20000), atol=1e-5)
+    assert g["shs"].shape == (20000, 4, 3)
+    g2 = synthetic.make_gaussians(20000, 1234)
+    assert all(torch.equal(g[k], g2[k]) for k in g)
+    cams = synthetic.orbit_cameras(4, 800, 800)
+    c = cams[0]
+    # MiniCam quirk (lightning/utils.py:48): camera_center = -c2w[:3, 3]
+    assert torch.allclose(c["camera_center"], -torch.tensor([1.70006549, 0.0, 0.8604804]))
+    # the scene origin projects to the image centre at depth ||t||
+    p = torch.tensor([0.0, 0.0, 0.0, 1.0]) @ c["full_proj_transform"]
+    assert abs(p[0] / p[3]) < 1e-5 and abs(p[1] / p[3]) < 1e-5
+    v = torch.tensor([0.0, 0.0, 0.0, 1.0]) @ c["world_view_transform"]
+    assert abs(v[2].item() - 1.9054) < 1e-3
+    # the orbit keeps the distance and looks at the origin from every pose
+    for c in cams:
+        v = torch.tensor([0.0, 0.0, 0.0, 1.0]) @ c["world_view_transform"]
+        assert abs(v[2].item() - 1.9054) < 1e-3 and abs(v[0].item()) < 1e-4 and abs(v[1].item()) < 1e-4
