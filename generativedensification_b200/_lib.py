@@ -19,6 +19,7 @@ _pi64 = C.POINTER(C.c_int64)
 
 GDR_OK = 0
 GRAD_MEANS2D, GRAD_MEANS3D, GRAD_COLOR, GRAD_OPACITY, GRAD_COV, GRAD_ALL = 1, 2, 4, 8, 16, 31
+FLAG_NO_TILE_CULL = 1
 
 # name -> (restype, argtypes); must list every symbol include/gdr.h declares
 SIGNATURES = {
@@ -30,8 +31,8 @@ SIGNATURES = {
     "gdr_sort_scratch_bytes": (_i, [_i64, _pi64]),
     "gdr_backward_scratch_bytes": (_i, [_i, _pi64]),
     "gdr_forward_project": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _i,
-                                 _vp, _vp, _vp, _vp, _vp]),
-    "gdr_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+                                 _vp, _vp, _vp, _vp, _i, _vp]),
+    "gdr_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
     "gdr_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp,
                           _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gdr_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),

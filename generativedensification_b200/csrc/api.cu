@@ -101,7 +101,7 @@ int gdr_forward_project(int P, int sh_degree, int M, int W, int H, const float* 
                         float scale_modifier, const float* rotations, const float* cov3D_precomp,
                         const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
                         float tan_fovy, int prefiltered, int32_t* radii, void* geom_state, void* image_state,
-                        int32_t* num_rendered_host, void* stream) {
+                        int32_t* num_rendered_host, int flags, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P < 0 || W <= 0 || H <= 0) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_forward_project: bad sizes");
     if (!image_state) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_forward_project: image_state is NULL");
@@ -135,6 +135,7 @@ int gdr_forward_project(int P, int sh_degree, int M, int W, int H, const float* 
         a.focal_y = H / (2.0f * tan_fovy);  // rasterizer_impl.cu:222-223
         a.focal_x = W / (2.0f * tan_fovx);
         a.prefiltered = prefiltered;
+        a.cull = (flags & GDR_FLAG_NO_TILE_CULL) ? 0 : 1;
         a.radii = radii;
         a.geom = gdr::GeomState::carve(geom_state, (size_t)P);
         a.img = img;
@@ -156,7 +157,7 @@ int gdr_forward_project(int P, int sh_degree, int M, int W, int H, const float* 
 
 int gdr_forward_render(int P, int W, int H, const float* bg, const int32_t* radii, const void* geom_state,
                        void* image_state, void* splat_stream, void* sort_scratch, int64_t capacity, float* out_color,
-                       float* out_depth, float* out_alpha, void* stream) {
+                       float* out_depth, float* out_alpha, int flags, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P < 0 || W <= 0 || H <= 0 || capacity < 0)
         return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_forward_render: bad sizes");
@@ -174,7 +175,7 @@ int gdr_forward_render(int P, int W, int H, const float* bg, const int32_t* radi
         // the emit cursors are zero here: tile_scan zeroes them and tile_sort re-zeroes them after use
         {
             StageTimer t(GDR_STAGE_EMIT, s);
-            GDR_CUDA(gdr::launch_emit(P, W, H, radii, geom, img, keys, capacity, s), "emit");
+            GDR_CUDA(gdr::launch_emit(P, W, H, radii, geom, img, keys, capacity, (flags & GDR_FLAG_NO_TILE_CULL) ? 0 : 1, s), "emit");
         }
         {
             StageTimer t(GDR_STAGE_TILE_SORT, s);

@@ -80,34 +80,46 @@ constexpr int EMIT_THREADS = 128;
 __global__ void __launch_bounds__(EMIT_THREADS)
 emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii, const Splat* __restrict__ splat,
             const uint32_t* __restrict__ tile_offsets, uint32_t* __restrict__ cursor, uint64_t* __restrict__ keys,
-            uint32_t* __restrict__ header, int64_t capacity) {
+            uint32_t* __restrict__ header, int64_t capacity, int cull) {
     const int idx = blockIdx.x * EMIT_THREADS + threadIdx.x;
     int n = 0, x0 = 0, y0 = 0, w = 0;
     uint32_t depth_bits = 0;
+    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
     if (idx < P) {
         const int r = radii[idx];
         if (r > 0) {
-            const float4 q0 = __ldg(&splat[idx].q0);
+            q0 = __ldg(&splat[idx].q0);
+            q1 = __ldg(&splat[idx].q1);
             int x1, y1;
             tile_rect(q0.x, q0.y, r, gx, gy, x0, y0, x1, y1);
             w = x1 - x0;
             n = w * (y1 - y0);
-            depth_bits = __float_as_uint(q0.z);
+            depth_bits = __float_as_uint(__ldg(&splat[idx].q2.w));
         }
     }
     const int lane = (int)lane_id();
     bool overflow = false;
-    warp_foreach_tile(n, x0, y0, w, gx, [&](int tile, int owner, int, bool valid, unsigned active) {
+    warp_foreach_tile(n, x0, y0, w, gx, [&](int tile, int owner, int, bool valid, unsigned) {
         const uint32_t o_depth = __shfl_sync(0xffffffffu, depth_bits, owner);
         const int o_idx = __shfl_sync(0xffffffffu, idx, owner);
-        if (valid) {
+        bool keep = valid;
+        if (cull) {  // the identical test project_kernel used when it counted this tile
+            const float cx = __shfl_sync(0xffffffffu, q0.x, owner), cy = __shfl_sync(0xffffffffu, q0.y, owner);
+            const float thr = __shfl_sync(0xffffffffu, q0.z, owner);
+            const float A = __shfl_sync(0xffffffffu, q1.x, owner), B = __shfl_sync(0xffffffffu, q1.y, owner);
+            const float C = __shfl_sync(0xffffffffu, q1.z, owner);
+            const float tx0 = (float)((tile % gx) * TILE), ty0 = (float)((tile / gx) * TILE);
+            keep = valid && !splat_misses_rect(cx, cy, A, B, C, thr, tx0, ty0, tx0 + (TILE - 1), ty0 + (TILE - 1));
+        }
+        const unsigned active = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
             const unsigned peers = __match_any_sync(active, tile);
             const int leader = __ffs(peers) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(&cursor[tile], (unsigned)__popc(peers));
             base = __shfl_sync(peers, base, leader);
             const uint64_t pos = (uint64_t)__ldg(&tile_offsets[tile]) + base + __popc(peers & lanemask_lt());
-            if ((int64_t)pos < capacity)
+            if ((int64_t)pos < capacity && pos < (uint64_t)__ldg(&tile_offsets[tile + 1]))
                 keys[pos] = ((uint64_t)o_depth << 32) | (uint32_t)o_idx;
             else
                 overflow = true;
@@ -225,11 +237,11 @@ cudaError_t launch_tile_scan(int T, ImageState img, cudaStream_t s) {
 }
 
 cudaError_t launch_emit(int P, int W, int H, const int32_t* radii, GeomState geom, ImageState img, uint64_t* keys,
-                        int64_t capacity, cudaStream_t s) {
+                        int64_t capacity, int cull, cudaStream_t s) {
     if (P <= 0) return cudaSuccess;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     emit_kernel<<<(P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(
-        P, gx, gy, radii, geom.splat, img.tile_offsets, img.tile_counter, keys, img.header, capacity);
+        P, gx, gy, radii, geom.splat, img.tile_offsets, img.tile_counter, keys, img.header, capacity, cull);
     return cudaGetLastError();
 }
 

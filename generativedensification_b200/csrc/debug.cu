@@ -16,7 +16,7 @@ __global__ void unpack_geom_kernel(int P, GeomState g, float* means2D, float* de
         means2D[2 * i] = s.q0.x;
         means2D[2 * i + 1] = s.q0.y;
     }
-    if (depths) depths[i] = s.q0.z;
+    if (depths) depths[i] = s.q2.w;
     if (conic_opacity) reinterpret_cast<float4*>(conic_opacity)[i] = s.q1;
     if (rgb) {
         rgb[3 * i] = s.q2.x;

@@ -22,6 +22,7 @@ struct ProjectArgs {
     const float* campos;
     float tan_fovx, tan_fovy, focal_x, focal_y;
     int prefiltered;
+    int cull;  // exact tile-level culling of (Gaussian, tile) pairs that cannot reach alpha = 1/255
     int32_t* radii;
     GeomState geom;
     ImageState img;
@@ -35,7 +36,7 @@ cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewma
 // binning.cu: tile scan, instance emission, per-tile depth sort + record gather
 cudaError_t launch_tile_scan(int T, ImageState img, cudaStream_t s);
 cudaError_t launch_emit(int P, int W, int H, const int32_t* radii, GeomState geom, ImageState img, uint64_t* keys,
-                        int64_t capacity, cudaStream_t s);
+                        int64_t capacity, int cull, cudaStream_t s);
 cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint64_t* keys, uint64_t* keys_alt,
                              Splat* stream, int64_t capacity, cudaStream_t s);
 

@@ -169,9 +169,10 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
     __syncthreads();
 
     int n_tiles = 0, rx0 = 0, ry0 = 0, rw = 0;
+    Splat rec;
+    rec.q0 = rec.q1 = rec.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (in_range) {
         int radius_out = 0;
-        Splat rec;
         rec.q0 = make_float4(0.f, 0.f, 0.f, __int_as_float(idx));
         rec.q1 = make_float4(0.f, 0.f, 0.f, 0.f);
         rec.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -220,11 +221,13 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
                     const float opacity = __ldg(a.opacities + idx);
                     // Conservative reject threshold: power < thr  =>  opacity*exp(power) < 1/255 for certain
                     // (1e-4 of slack in the exponent dwarfs every rounding error of the exact test).
-                    const float thr = opacity > 0.f ? (logf(ALPHA_MIN / opacity) - 1e-4f) : (opacity <= 0.f ? INFINITY : 0.0f);
+                    // (opacity <= 0 can never reach 1/255: reject everything; NaN opacity: never reject.)
+                    const float thr = opacity > 0.f ? (logf(ALPHA_MIN / opacity) - 1e-4f)
+                                                    : (opacity <= 0.f ? INFINITY : -INFINITY);
                     radius_out = (int)my_radius;
-                    rec.q0 = make_float4(pix.x, pix.y, p_view.z, __int_as_float(idx));
+                    rec.q0 = make_float4(pix.x, pix.y, thr, __int_as_float(idx));
                     rec.q1 = make_float4(conic.x, conic.y, conic.z, opacity);
-                    rec.q2 = make_float4(rgb.x, rgb.y, rgb.z, thr);
+                    rec.q2 = make_float4(rgb.x, rgb.y, rgb.z, p_view.z);
                     rx0 = x0;
                     ry0 = y0;
                     rw = x1 - x0;
@@ -247,9 +250,23 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
     }
 
     // ---- bin counters: one aggregated atomic per distinct tile per warp step ----
+    // With culling on, a (Gaussian, tile) pair is only counted if the splat can reach alpha >= 1/255
+    // somewhere in the tile (exact: see splat_misses_rect); emit_kernel applies the identical test.
     uint32_t* counter = a.img.tile_counter;
-    warp_foreach_tile(n_tiles, rx0, ry0, rw, a.gx, [&](int tile, int, int, bool valid, unsigned active) {
-        if (valid) {
+    const bool cull = a.cull != 0;
+    const int gx = a.gx;
+    warp_foreach_tile(n_tiles, rx0, ry0, rw, gx, [&](int tile, int owner, int, bool valid, unsigned) {
+        bool keep = valid;
+        if (cull) {
+            const float cx = __shfl_sync(0xffffffffu, rec.q0.x, owner), cy = __shfl_sync(0xffffffffu, rec.q0.y, owner);
+            const float thr = __shfl_sync(0xffffffffu, rec.q0.z, owner);
+            const float A = __shfl_sync(0xffffffffu, rec.q1.x, owner), B = __shfl_sync(0xffffffffu, rec.q1.y, owner);
+            const float C = __shfl_sync(0xffffffffu, rec.q1.z, owner);
+            const float tx0 = (float)((tile % gx) * TILE), ty0 = (float)((tile / gx) * TILE);
+            keep = valid && !splat_misses_rect(cx, cy, A, B, C, thr, tx0, ty0, tx0 + (TILE - 1), ty0 + (TILE - 1));
+        }
+        const unsigned active = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
             const unsigned peers = __match_any_sync(active, tile);
             if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&counter[tile], (unsigned)__popc(peers));
         }

@@ -74,6 +74,11 @@ extern "C" {
 #define GDR_GRAD_COV 16    /* dL/dscales + dL/drotations, or dL/dcov3D_precomp */
 #define GDR_GRAD_ALL 31
 
+/* flags for gdr_forward_project / gdr_forward_render (must be identical in both calls of a frame) */
+#define GDR_FLAG_NO_TILE_CULL 1 /* bin every tile of the reference's 3-sigma rectangle, exactly like the reference.
+                                   Default (0): drop (Gaussian, tile) pairs that provably cannot reach
+                                   alpha = 1/255 in the tile -- outputs are unchanged, R shrinks. */
+
 GDR_API int gdr_abi_version(void);
 GDR_API const char* gdr_last_error(void);
 
@@ -92,13 +97,13 @@ GDR_API int gdr_forward_project(int P, int sh_degree, int M, int W, int H,
                         const float* viewmatrix, const float* projmatrix, const float* campos,
                         float tan_fovx, float tan_fovy, int prefiltered,
                         int32_t* radii /* out [P] */, void* geom_state, void* image_state,
-                        int32_t* num_rendered_host /* pinned host memory or NULL */, void* stream);
+                        int32_t* num_rendered_host /* pinned host memory or NULL */, int flags, void* stream);
 
 /* Step 2 of the forward (replaces rasterizer_impl.cu:284-337). out_* are [3,H,W], [1,H,W], [1,H,W]. */
 GDR_API int gdr_forward_render(int P, int W, int H, const float* bg, const int32_t* radii,
                        const void* geom_state, void* image_state,
                        void* splat_stream, void* sort_scratch, int64_t capacity,
-                       float* out_color, float* out_depth, float* out_alpha, void* stream);
+                       float* out_color, float* out_depth, float* out_alpha, int flags, void* stream);
 
 /* Backward (replaces Rasterizer::backward, rasterizer_impl.cu:343-447).  dL_dout_depth / dL_dout_alpha
  * may be NULL (treated as zero).  Output gradient pointers may be NULL when the matching bit of

@@ -24,11 +24,37 @@ IMG_TOL = 1e-4
 GRAD_TOL = 1e-3
 
 
+def _is_subsequence_per_tile(ours_list, ours_ranges, ref_list, ref_ranges):
+    """Every tile's (culled) list must be an order-preserving subsequence of the reference's list."""
+    for t in range(ref_ranges.shape[0]):
+        a = ours_list[ours_ranges[t, 0]:ours_ranges[t, 1]]
+        b = ref_list[ref_ranges[t, 0]:ref_ranges[t, 1]]
+        pos = {int(v): i for i, v in enumerate(b)}
+        idx = [pos.get(int(v), -1) for v in a]
+        if any(i < 0 for i in idx) or any(x >= y for x, y in zip(idx, idx[1:])):
+            return False
+    return True
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_forward_with_exact_tile_culling(name, device):
+    """Default mode: (Gaussian, tile) pairs that cannot reach alpha = 1/255 are dropped -- outputs must not move."""
+    g = U.load_golden(name)
+    sc = U.scene_from_golden(g)
+    o = U.run_ours(sc, device, tile_cull=True)
+    assert np.array_equal(o["radii"], g["radii"])
+    assert int(o["num_rendered"]) <= int(g["num_rendered"])
+    assert _is_subsequence_per_tile(o["point_list"], o["ranges"], g["point_list"], g["ranges"])
+    assert U.max_abs(o["depth"], g["depth"]) == 0.0
+    assert U.max_abs(o["alpha"], g["alpha"]) == 0.0
+    assert U.max_abs(o["color"], g["color"]) <= 2e-6
+
+
 @pytest.mark.parametrize("name", GOLDEN)
 def test_golden_forward(name, device):
     g = U.load_golden(name)
     sc = U.scene_from_golden(g)
-    o = U.run_ours(sc, device)
+    o = U.run_ours(sc, device, tile_cull=False)
     assert np.array_equal(o["radii"], g["radii"])
     assert int(o["num_rendered"]) == int(g["num_rendered"])
     vis = g["radii"] > 0
@@ -69,12 +95,16 @@ def test_vs_oracle_fresh_scenes(seed, P, W, H, deg, device):
                    log_scale=math.log(0.03), opacity_mean=0.5)
     grads = SC.upstream_grads(sc, seed=seed)
     st, og = U.run_oracle(sc, grads)
+    o_ref_bins = U.run_ours(sc, device, tile_cull=False)
     o = U.run_ours(sc, device, grads=grads)
     amb_g = st.ambiguous_gauss > 0
     assert np.array_equal(o["radii"][~amb_g], st.radii[~amb_g])
     if not amb_g.any():
-        assert np.array_equal(o["point_list"], st.point_list)
-        assert np.array_equal(o["ranges"], st.ranges)
+        assert np.array_equal(o_ref_bins["point_list"], st.point_list)
+        assert np.array_equal(o_ref_bins["ranges"], st.ranges)
+        assert int(o["num_rendered"]) <= st.num_rendered
+    for k in ("color", "depth", "alpha"):  # culling changes no output bit
+        assert np.array_equal(o[k], o_ref_bins[k])
     ok = st.ambiguous_pix == 0
     assert (~ok).mean() <= 0.02
     for mine, ref in ((o["color"], st.color), (o["depth"], st.depth), (o["alpha"], st.alpha)):
@@ -146,7 +176,7 @@ def test_capacity_misprediction_is_rerun(device):
 
     sc = SC._scene("cap", 4000, 128, 128, 12, log_scale=math.log(0.03))
     a = _render(sc, device)
-    key = (device.index, 4000, 128, 128)
+    key = (device.index, 4000, 128, 128, 0)
     assert Rz._predictor.last[key] > 0
     Rz._predictor.last[key] = 10  # next call speculates with a capacity far too small
     b = _render(sc, device)
@@ -165,7 +195,7 @@ def test_long_tile_lists_take_the_merge_path(device):
     sc["means3D"] = sc["means3D"] * 0.08  # everything lands in the central tiles of a 2x2-tile image
     grads = SC.upstream_grads(sc)
     st, og = U.run_oracle(sc, grads)
-    o = U.run_ours(sc, device, grads=grads)
+    o = U.run_ours(sc, device, grads=grads, tile_cull=False)
     assert (st.ranges[:, 1].astype(np.int64) - st.ranges[:, 0]).max() > 4096
     assert np.array_equal(o["point_list"], st.point_list)
     assert np.array_equal(o["ranges"], st.ranges)
@@ -273,11 +303,15 @@ def test_full_size_vs_compiled_reference(P, V, backward, device):
         sc = dict(name="full", camera=cam, bg=torch.ones(3), sh_degree=1, scale_modifier=1.0, colors_precomp=None,
                   cov3D_precomp=None, **g)
         r = MG.run_reference(ref, sc, device)
-        o = U.run_ours(sc, device, grads=SC.upstream_grads(sc, seed=1237) if backward else None)
+        o_ref_bins = U.run_ours(sc, device, tile_cull=False)
+        assert int(o_ref_bins["num_rendered"]) == int(r["num_rendered"])
+        assert np.array_equal(o_ref_bins["point_list"], r["point_list"])
+        assert np.array_equal(o_ref_bins["n_contrib"], r["n_contrib"])
+        o = U.run_ours(sc, device, grads=SC.upstream_grads(sc) if backward else None)
         assert np.array_equal(o["radii"], r["radii"])
-        assert int(o["num_rendered"]) == int(r["num_rendered"])
-        assert np.array_equal(o["point_list"], r["point_list"])
-        assert np.array_equal(o["n_contrib"], r["n_contrib"])
+        assert int(o["num_rendered"]) < int(r["num_rendered"])
+        for k in ("color", "depth", "alpha"):
+            assert np.array_equal(o[k], o_ref_bins[k])
         for k in ("color", "depth", "alpha"):
             assert U.max_abs(o[k], r[k]) <= IMG_TOL, k
         assert abs(U.psnr(o["color"], r["color"])) >= 90.0

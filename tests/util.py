@@ -61,10 +61,24 @@ def run_oracle(sc, grads=None):
     return st, g
 
 
-def run_ours(sc, device, grads=None, with_state=True):
+def run_ours(sc, device, grads=None, with_state=True, tile_cull=None):
     """Render with the CUDA path through the public API; optionally backprop `grads` = (gc, gd, ga).
 
-    Returns a dict with the same keys as tests/golden/make_golden.py writes."""
+    tile_cull: None = library default (on); False = bin exactly the reference's tile rectangles, so that the
+    internal lists can be compared with the reference's.  Returns the keys tests/golden/make_golden.py writes."""
+    from generativedensification_b200 import rasterizer as Rz
+
+    if tile_cull is None:
+        return _run_ours(sc, device, grads, with_state)
+    old = Rz.options["tile_cull"]
+    Rz.options["tile_cull"] = bool(tile_cull)
+    try:
+        return _run_ours(sc, device, grads, with_state)
+    finally:
+        Rz.options["tile_cull"] = old
+
+
+def _run_ours(sc, device, grads=None, with_state=True):
     from generativedensification_b200 import _lib, synthetic as S
     from generativedensification_b200.rasterizer import GaussianRasterizer, _forward_impl
 
