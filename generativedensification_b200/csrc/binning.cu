@@ -34,7 +34,11 @@ constexpr int SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageState img) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t warp_max[32];
+    __shared__ uint32_t bucket_count[33];  // tiles per floor(log2(count)) + 1 bucket; bucket 0 = empty tiles
+    __shared__ uint32_t bucket_base[33];
     const int tid = threadIdx.x;
+    if (tid < 33) bucket_count[tid] = 0;
+    __syncthreads();
     const int per = (T + SCAN_THREADS - 1) / SCAN_THREADS;
     const int b = min(T, tid * per), e = min(T, b + per);
     uint32_t local = 0, lmax = 0;
@@ -42,6 +46,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageSta
         const uint32_t c = img.tile_counter[i];
         local += c;
         lmax = max(lmax, c);
+        atomicAdd(&bucket_count[c ? 32 - __clz(c) : 0], 1u);
     }
     // block exclusive scan of `local`
     const int lane = tid & 31, wid = tid >> 5;
@@ -65,6 +70,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageSta
         }
         if (lane == 0) img.header[HDR_MAX_TILE] = mm;
     }
+    if (tid == 0) {  // heaviest bucket first: longest-processing-time-first order for the blend kernels
+        uint32_t acc = 0;
+        for (int k = 32; k >= 0; k--) {
+            bucket_base[k] = acc;
+            acc += bucket_count[k];
+        }
+    }
     __syncthreads();
     uint32_t run = warp_sums[wid] + (uint32_t)incl - local;
     for (int i = b; i < e; i++) {
@@ -72,6 +84,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageSta
         img.tile_offsets[i] = run;
         img.tile_counter[i] = 0;  // becomes the emit cursor
         run += c;
+        img.tile_order[atomicAdd(&bucket_base[c ? 32 - __clz(c) : 0], 1u)] = (uint32_t)i;
     }
 }
 

@@ -44,14 +44,14 @@ __device__ __forceinline__ unsigned subblock_mask(float lx, float ly, float4 con
 }
 
 __global__ void __launch_bounds__(BLEND_THREADS)
-blend_forward_kernel(int W, int H, int gx, const float* __restrict__ bg, const uint32_t* __restrict__ tile_offsets,
+blend_forward_kernel(int W, int H, int gx, const float* __restrict__ bg, const uint32_t* __restrict__ tile_offsets, const uint32_t* __restrict__ tile_order,
                      const Splat* __restrict__ stream, int64_t capacity, uint32_t* __restrict__ n_contrib,
                      float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha) {
     __shared__ __align__(128) Splat buf[2][CHUNK];
     __shared__ __align__(8) uint64_t full[2];
     __shared__ uint8_t s_mask[CHUNK];
 
-    const int tile = blockIdx.x;
+    const int tile = (int)tile_order[blockIdx.x];  // heaviest tiles first
     const int tile_x = tile % gx, tile_y = tile / gx;
     const int64_t rb = min((int64_t)tile_offsets[tile], capacity);
     const int64_t re = min((int64_t)tile_offsets[tile + 1], capacity);
@@ -164,7 +164,7 @@ cudaError_t launch_blend_forward(int W, int H, const float* bg, ImageState img, 
                                  int64_t capacity, float* out_color, float* out_depth, float* out_alpha,
                                  cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    blend_forward_kernel<<<gx * gy, BLEND_THREADS, 0, s>>>(W, H, gx, bg, img.tile_offsets, stream, capacity,
+    blend_forward_kernel<<<gx * gy, BLEND_THREADS, 0, s>>>(W, H, gx, bg, img.tile_offsets, img.tile_order, stream, capacity,
                                                            img.n_contrib, out_color, out_depth, out_alpha);
     return cudaGetLastError();
 }

@@ -9,6 +9,7 @@
 //     uint32   header[64]               header[0] = R (instances), header[1] = overflow flag
 //     uint32   tile_offsets[T + 1]      exclusive scan of per-tile instance counts (the reference's `ranges`)
 //     uint32   tile_counter[T]          bin counters (count pass, then emit cursors)
+//     uint32   tile_order[T]            tiles in decreasing-work order (blend kernels: blockIdx -> tile)
 //     uint32   n_contrib[H * W]
 // SplatStream (reference: BinningState.point_list, but materialised):
 //     Splat    stream[capacity]         per-tile, depth-sorted copies of the Gaussians' records,
@@ -58,12 +59,14 @@ struct ImageState {
     uint32_t* header;
     uint32_t* tile_offsets;
     uint32_t* tile_counter;
+    uint32_t* tile_order;
     uint32_t* n_contrib;
     static __host__ __device__ size_t bytes(int W, int H) {
         const size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
         size_t o = 0;
         o = align_up(o + 4 * IMG_HEADER_WORDS, 256);
         o = align_up(o + 4 * (T + 1), 256);
+        o = align_up(o + 4 * T, 256);
         o = align_up(o + 4 * T, 256);
         o = align_up(o + 4 * (size_t)W * H, 256);
         return o + 256;
@@ -78,6 +81,8 @@ struct ImageState {
         s.tile_offsets = (uint32_t*)(p + o);
         o = align_up(o + 4 * (T + 1), 256);
         s.tile_counter = (uint32_t*)(p + o);
+        o = align_up(o + 4 * T, 256);
+        s.tile_order = (uint32_t*)(p + o);
         o = align_up(o + 4 * T, 256);
         s.n_contrib = (uint32_t*)(p + o);
         return s;
