@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(EMIT_THREADS)
 emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii, const Splat* __restrict__ splat,
             const uint32_t* __restrict__ tile_offsets, uint32_t* __restrict__ cursor, uint64_t* __restrict__ keys,
             uint32_t* __restrict__ header, int64_t capacity, int cull) {
-    const int idx = blockIdx.x * EMIT_THREADS + threadIdx.x;
+    const int n_vblocks = (P + EMIT_THREADS - 1) / EMIT_THREADS;
+    bool overflow = false;
+    for (int vb = blockIdx.x; vb < n_vblocks; vb += gridDim.x) {  // virtual blocks: balanced single wave
+    const int idx = vb * EMIT_THREADS + threadIdx.x;
     int n = 0, x0 = 0, y0 = 0, w = 0;
     uint32_t depth_bits = 0;
     float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
@@ -111,7 +114,6 @@ emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii, const Spla
         }
     }
     const int lane = (int)lane_id();
-    bool overflow = false;
     warp_foreach_tile(n, x0, y0, w, gx, [&](int tile, int owner, int, bool valid, unsigned) {
         const uint32_t o_depth = __shfl_sync(0xffffffffu, depth_bits, owner);
         const int o_idx = __shfl_sync(0xffffffffu, idx, owner);
@@ -138,6 +140,7 @@ emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii, const Spla
                 overflow = true;
         }
     });
+    }  // virtual blocks
     if (overflow) atomicOr(&header[HDR_OVERFLOW], 1u);
 }
 
@@ -253,7 +256,11 @@ cudaError_t launch_emit(int P, int W, int H, const int32_t* radii, GeomState geo
                         int64_t capacity, int cull, cudaStream_t s) {
     if (P <= 0) return cudaSuccess;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    emit_kernel<<<(P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel, EMIT_THREADS, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    const int grid = min((P + EMIT_THREADS - 1) / EMIT_THREADS, sm_count() * per_sm);
+    emit_kernel<<<grid, EMIT_THREADS, 0, s>>>(
         P, gx, gy, radii, geom.splat, img.tile_offsets, img.tile_counter, keys, img.header, capacity, cull);
     return cudaGetLastError();
 }

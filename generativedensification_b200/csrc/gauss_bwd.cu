@@ -32,9 +32,14 @@ __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y 
 
 constexpr int GB_THREADS = 128;
 
+__device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, const int idx);
+
 __global__ void __launch_bounds__(GB_THREADS) gauss_backward_kernel(const GaussBackwardArgs a) {
-    const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
-    if (idx >= a.P) return;
+    for (int idx = blockIdx.x * GB_THREADS + threadIdx.x; idx < a.P; idx += gridDim.x * GB_THREADS)
+        gauss_backward_one(a, idx);
+}
+
+__device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, const int idx) {
     const float4* acc = reinterpret_cast<const float4*>(a.accum + (size_t)idx * 12);
     const float4 g_mean2D = acc[0];
     const float4 g_conic_op = acc[1];
@@ -311,7 +316,12 @@ __global__ void __launch_bounds__(GB_THREADS) gauss_backward_kernel(const GaussB
 
 cudaError_t launch_gauss_backward(const GaussBackwardArgs& a, cudaStream_t s) {
     if (a.P <= 0) return cudaSuccess;
-    gauss_backward_kernel<<<(a.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(a);
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gauss_backward_kernel, GB_THREADS, 0) != cudaSuccess ||
+        per_sm < 1)
+        per_sm = 1;
+    const int grid = min((a.P + GB_THREADS - 1) / GB_THREADS, sm_count() * per_sm);
+    gauss_backward_kernel<<<grid, GB_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -7,6 +7,10 @@
 
 namespace gdr {
 
+// Number of SMs of the current device (cached); grids of the per-Gaussian kernels are sized as a
+// multiple of it and loop over virtual blocks, so no kernel ends with a nearly empty last wave.
+int sm_count();
+
 struct ProjectArgs {
     int P, sh_degree, M, W, H, gx, gy;
     const float* means3D;

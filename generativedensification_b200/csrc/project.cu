@@ -153,7 +153,10 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, float3 pos, float3 campos, 
 
 __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs a) {
     extern __shared__ __align__(16) float smem[];
-    const int first = blockIdx.x * PROJ_THREADS;
+    const int n_vblocks = (a.P + PROJ_THREADS - 1) / PROJ_THREADS;
+    for (int vb = blockIdx.x; vb < n_vblocks; vb += gridDim.x) {  // virtual blocks: balanced single wave
+    if (vb != (int)blockIdx.x) __syncthreads();                  // the staging buffers are reused
+    const int first = vb * PROJ_THREADS;
     const int n_items = min(PROJ_THREADS, a.P - first);
     const int idx = first + threadIdx.x;
     const bool in_range = threadIdx.x < n_items;
@@ -271,6 +274,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
             if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&counter[tile], (unsigned)__popc(peers));
         }
     });
+    }  // virtual blocks
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
@@ -284,6 +288,16 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 
 }  // namespace
 
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 cudaError_t launch_project(const ProjectArgs& a, cudaStream_t s) {
     if (a.P <= 0) return cudaSuccess;
     const size_t smem = sizeof(float) * PROJ_THREADS * (6 + 3 * (size_t)(a.colors_precomp ? 0 : a.M));
@@ -291,7 +305,12 @@ cudaError_t launch_project(const ProjectArgs& a, cudaStream_t s) {
         cudaError_t e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const int grid = (a.P + PROJ_THREADS - 1) / PROJ_THREADS;
+    const int n_vblocks = (a.P + PROJ_THREADS - 1) / PROJ_THREADS;
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, project_kernel, PROJ_THREADS, smem) != cudaSuccess ||
+        per_sm < 1)
+        per_sm = 1;
+    const int grid = min(n_vblocks, sm_count() * per_sm);
     project_kernel<<<grid, PROJ_THREADS, smem, s>>>(a);
     return cudaGetLastError();
 }
