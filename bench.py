@@ -351,4 +351,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        from generativedensification_b200 import shard as _shard
+
+        _shard.shutdown()
