@@ -20,6 +20,7 @@ _pi64 = C.POINTER(C.c_int64)
 GDR_OK = 0
 GRAD_MEANS2D, GRAD_MEANS3D, GRAD_COLOR, GRAD_OPACITY, GRAD_COV, GRAD_ALL = 1, 2, 4, 8, 16, 31
 FLAG_NO_TILE_CULL = 1
+CAMERA_FLOATS = 48
 
 # name -> (restype, argtypes); must list every symbol include/gdr.h declares
 SIGNATURES = {
@@ -35,6 +36,11 @@ SIGNATURES = {
     "gdr_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
     "gdr_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp,
                           _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gdr_views_forward_project": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _vp, _vp,
+                                       _vp, _vp, _i, _vp]),
+    "gdr_views_forward_render": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
+    "gdr_views_backward": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
+                                _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gdr_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "gdr_debug_unpack_geom": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gdr_debug_unpack_bins": (_i, [_i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),

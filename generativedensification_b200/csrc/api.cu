@@ -96,46 +96,79 @@ int gdr_backward_scratch_bytes(int P, int64_t* bytes) {
     return GDR_OK;
 }
 
-int gdr_forward_project(int P, int sh_degree, int M, int W, int H, const float* means3D, const float* shs,
-                        const float* colors_precomp, const float* opacities, const float* scales,
-                        float scale_modifier, const float* rotations, const float* cov3D_precomp,
-                        const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
-                        float tan_fovy, int prefiltered, int32_t* radii, void* geom_state, void* image_state,
-                        int32_t* num_rendered_host, int flags, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
-    if (P < 0 || W <= 0 || H <= 0) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_forward_project: bad sizes");
-    if (!image_state) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_forward_project: image_state is NULL");
+}  // extern "C"
+
+// ---- shared implementation of the single-view and the batched entry points -------------------------
+namespace {
+
+struct GaussianInputs {
+    const float *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *cov3D_precomp;
+    float scale_modifier;
+};
+
+gdr::Views single_view(int P, int W, int H, const float* viewmatrix, const float* projmatrix, const float* campos,
+                       const float* bg, float tan_fovx, float tan_fovy) {
+    gdr::Views vw;
+    vw.V = 1;
+    vw.geom_stride = vw.img_stride = vw.cam_stride = 0;
+    vw.view = viewmatrix; vw.proj = projmatrix; vw.campos = campos; vw.bg = bg;
+    vw.tanfov = nullptr; vw.tan_fovx = tan_fovx; vw.tan_fovy = tan_fovy;
+    (void)P; (void)W; (void)H;
+    return vw;
+}
+
+gdr::Views batched_views(int V, int P, int W, int H, const gdr_camera* cams) {
+    gdr::Views vw;
+    const float* c = reinterpret_cast<const float*>(cams);
+    vw.V = V;
+    vw.geom_stride = gdr::GeomState::bytes((size_t)P);
+    vw.img_stride = gdr::ImageState::bytes(W, H);
+    vw.cam_stride = GDR_CAMERA_FLOATS;
+    vw.view = c; vw.proj = c + 16; vw.campos = c + 32; vw.tanfov = c + 35; vw.bg = c + 37;
+    vw.tan_fovx = vw.tan_fovy = 0.f;
+    return vw;
+}
+
+int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, int M, int W, int H, const GaussianInputs& g,
+                 int prefiltered, int32_t* radii, void* geom_state, void* image_state, int32_t* num_rendered_host,
+                 int flags, cudaStream_t s) {
+    if (P < 0 || W <= 0 || H <= 0 || vw.V <= 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
+    if (!image_state) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: image_state is NULL", who);
     if (P > 0) {
-        if (!means3D || !opacities || !radii || !geom_state || !viewmatrix || !projmatrix)
-            return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_forward_project: a required pointer is NULL");
-        if (!shs && !colors_precomp)
-            return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_forward_project: provide SHs or precomputed colors");
-        if (!colors_precomp && (!campos || M <= 0 || (sh_degree + 1) * (sh_degree + 1) > M || sh_degree < 0 ||
-                                sh_degree > 3))
-            return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_forward_project: SH degree / coefficient count mismatch");
-        if (!cov3D_precomp && (!scales || !rotations))
-            return fail(GDR_ERR_INVALID_ARGUMENT,
-                        "gdr_forward_project: provide scales+rotations or a precomputed 3D covariance");
-        if (!cov3D_precomp && (((uintptr_t)rotations) & 15u))
-            return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_forward_project: rotations must be 16-byte aligned");
+        if (!g.means3D || !g.opacities || !radii || !geom_state || !vw.view || !vw.proj)
+            return fail(GDR_ERR_INVALID_ARGUMENT, "%s: a required pointer is NULL", who);
+        if (!g.shs && !g.colors_precomp)
+            return fail(GDR_ERR_INVALID_ARGUMENT, "%s: provide SHs or precomputed colors", who);
+        if (!g.colors_precomp && (!vw.campos || M <= 0 || (sh_degree + 1) * (sh_degree + 1) > M || sh_degree < 0 ||
+                                  sh_degree > 3))
+            return fail(GDR_ERR_INVALID_ARGUMENT, "%s: SH degree / coefficient count mismatch", who);
+        if (!g.cov3D_precomp && (!g.scales || !g.rotations))
+            return fail(GDR_ERR_INVALID_ARGUMENT, "%s: provide scales+rotations or a precomputed 3D covariance", who);
+        if (!g.cov3D_precomp && (((uintptr_t)g.rotations) & 15u))
+            return fail(GDR_ERR_INVALID_ARGUMENT, "%s: rotations must be 16-byte aligned", who);
     }
     gdr::ImageState img = gdr::ImageState::carve(image_state, W, H);
     const int T = tiles_of(W, H);
-    GDR_CUDA(cudaMemsetAsync(img.header, 0, sizeof(uint32_t) * gdr::IMG_HEADER_WORDS, s), "memset(header)");
-    GDR_CUDA(cudaMemsetAsync(img.tile_counter, 0, sizeof(uint32_t) * (size_t)T, s), "memset(tile_counter)");
+    const size_t hdr_bytes = sizeof(uint32_t) * gdr::IMG_HEADER_WORDS, cnt_bytes = sizeof(uint32_t) * (size_t)T;
+    if (vw.V == 1) {
+        GDR_CUDA(cudaMemsetAsync(img.header, 0, hdr_bytes, s), "memset(header)");
+        GDR_CUDA(cudaMemsetAsync(img.tile_counter, 0, cnt_bytes, s), "memset(tile_counter)");
+    } else {  // one strided memset over the V per-view states
+        GDR_CUDA(cudaMemset2DAsync(img.header, vw.img_stride, 0, hdr_bytes, (size_t)vw.V, s), "memset(header)");
+        GDR_CUDA(cudaMemset2DAsync(img.tile_counter, vw.img_stride, 0, cnt_bytes, (size_t)vw.V, s),
+                 "memset(tile_counter)");
+    }
     if (P > 0) {
         gdr::ProjectArgs a;
         a.P = P; a.sh_degree = sh_degree; a.M = M; a.W = W; a.H = H;
         a.gx = (W + gdr::TILE - 1) / gdr::TILE;
         a.gy = (H + gdr::TILE - 1) / gdr::TILE;
-        a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.opacities = opacities;
-        a.scales = scales; a.scale_modifier = scale_modifier; a.rotations = rotations;
-        a.cov3D_precomp = cov3D_precomp; a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.campos = campos;
-        a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
-        a.focal_y = H / (2.0f * tan_fovy);  // rasterizer_impl.cu:222-223
-        a.focal_x = W / (2.0f * tan_fovx);
+        a.means3D = g.means3D; a.shs = g.shs; a.colors_precomp = g.colors_precomp; a.opacities = g.opacities;
+        a.scales = g.scales; a.scale_modifier = g.scale_modifier; a.rotations = g.rotations;
+        a.cov3D_precomp = g.cov3D_precomp;
         a.prefiltered = prefiltered;
         a.cull = (flags & GDR_FLAG_NO_TILE_CULL) ? 0 : 1;
+        a.vw = vw;
         a.radii = radii;
         a.geom = gdr::GeomState::carve(geom_state, (size_t)P);
         a.img = img;
@@ -146,49 +179,122 @@ int gdr_forward_project(int P, int sh_degree, int M, int W, int H, const float* 
     }
     {
         StageTimer t(GDR_STAGE_TILE_SCAN, s);
-        GDR_CUDA(gdr::launch_tile_scan(T, img, s), "tile_scan");
+        GDR_CUDA(gdr::launch_tile_scan(T, img, vw, s), "tile_scan");
     }
     if (num_rendered_host)
-        GDR_CUDA(cudaMemcpyAsync(num_rendered_host, img.header + gdr::HDR_NUM_RENDERED, sizeof(int32_t),
-                                 cudaMemcpyDeviceToHost, s),
+        GDR_CUDA(cudaMemcpy2DAsync(num_rendered_host, sizeof(int32_t), img.header + gdr::HDR_NUM_RENDERED,
+                                   vw.V > 1 ? vw.img_stride : sizeof(int32_t), sizeof(int32_t), (size_t)vw.V,
+                                   cudaMemcpyDeviceToHost, s),
                  "memcpy(num_rendered)");
     return GDR_OK;
+}
+
+int render_impl(const char* who, const gdr::Views& vw, int P, int W, int H, const int32_t* radii, const void* geom_state,
+                void* image_state, void* splat_stream, void* sort_scratch, int64_t capacity, float* out_color,
+                float* out_depth, float* out_alpha, int flags, cudaStream_t s) {
+    if (P < 0 || W <= 0 || H <= 0 || capacity < 0 || vw.V <= 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
+    if (!image_state || !vw.bg || !out_color || !out_depth || !out_alpha)
+        return fail(GDR_ERR_INVALID_ARGUMENT, "%s: a required pointer is NULL", who);
+    if (capacity > 0 && (!splat_stream || !sort_scratch))
+        return fail(GDR_ERR_INVALID_ARGUMENT, "%s: stream/scratch is NULL with capacity > 0", who);
+    if (P > 0 && (!geom_state || !radii)) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: geom_state is NULL", who);
+    gdr::ImageState img = gdr::ImageState::carve(image_state, W, H);
+    gdr::Splat* strm = (gdr::Splat*)splat_stream;
+    if (P > 0 && capacity > 0) {
+        gdr::GeomState geom = gdr::GeomState::carve(const_cast<void*>(geom_state), (size_t)P);
+        const size_t total = (size_t)capacity * (size_t)vw.V;
+        uint64_t* keys = (uint64_t*)sort_scratch;
+        uint64_t* keys_alt = (uint64_t*)((char*)sort_scratch + gdr::align_up(sizeof(uint64_t) * total, 256));
+        // the emit cursors are zero here: tile_scan zeroes them and tile_sort re-zeroes them after use
+        {
+            StageTimer t(GDR_STAGE_EMIT, s);
+            GDR_CUDA(gdr::launch_emit(P, W, H, radii, geom, img, keys, capacity, (flags & GDR_FLAG_NO_TILE_CULL) ? 0 : 1,
+                                      vw, s),
+                     "emit");
+        }
+        {
+            StageTimer t(GDR_STAGE_TILE_SORT, s);
+            GDR_CUDA(gdr::launch_tile_sort(W, H, geom, img, keys, keys_alt, strm, capacity, vw, s), "tile_sort");
+        }
+    }
+    {
+        StageTimer t(GDR_STAGE_BLEND_FWD, s);
+        GDR_CUDA(gdr::launch_blend_forward(W, H, img, strm, (P > 0) ? capacity : 0, out_color, out_depth, out_alpha, vw,
+                                           s),
+                 "blend_forward");
+    }
+    return GDR_OK;
+}
+
+struct GradOutputs {
+    float *means2D, *colors, *opacity, *means3D, *cov3D, *sh, *scales, *rotations;
+};
+
+int backward_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, int M, int W, int H,
+                  const GaussianInputs& g, const int32_t* radii, const void* geom_state, const void* image_state,
+                  const void* splat_stream, int64_t capacity, const float* out_alpha, const float* dL_dout_color,
+                  const float* dL_dout_depth, const float* dL_dout_alpha, void* backward_scratch, int grad_mask,
+                  const GradOutputs& o, cudaStream_t s) {
+    if (P < 0 || W <= 0 || H <= 0 || capacity < 0 || vw.V <= 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
+    if (P == 0) return GDR_OK;
+    if (!g.means3D || !radii || !geom_state || !image_state || !out_alpha || !dL_dout_color || !backward_scratch ||
+        !vw.view || !vw.proj || !vw.bg)
+        return fail(GDR_ERR_INVALID_ARGUMENT, "%s: a required pointer is NULL", who);
+    if (capacity > 0 && !splat_stream) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: splat_stream is NULL", who);
+    if ((((uintptr_t)backward_scratch) & 15u) || (o.means2D && (((uintptr_t)o.means2D) & 15u)) ||
+        (o.rotations && (((uintptr_t)o.rotations) & 15u)) || (g.rotations && (((uintptr_t)g.rotations) & 15u)))
+        return fail(GDR_ERR_INVALID_ARGUMENT, "%s: float4 buffers must be 16-byte aligned", who);
+    if (g.shs && !vw.campos) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: campos is NULL", who);
+    gdr::ImageState img = gdr::ImageState::carve(const_cast<void*>(image_state), W, H);
+    gdr::GeomState geom = gdr::GeomState::carve(const_cast<void*>(geom_state), (size_t)P);
+    float* accum = (float*)backward_scratch;
+    GDR_CUDA(cudaMemsetAsync(accum, 0, sizeof(float) * 12 * (size_t)P * (size_t)vw.V, s), "memset(accum)");
+    {
+        StageTimer t(GDR_STAGE_BLEND_BWD, s);
+        GDR_CUDA(gdr::launch_blend_backward(P, W, H, img, (const gdr::Splat*)splat_stream, capacity, out_alpha,
+                                            dL_dout_color, dL_dout_depth, dL_dout_alpha, accum, grad_mask, vw, s),
+                 "blend_backward");
+    }
+    gdr::GaussBackwardArgs a;
+    a.P = P; a.sh_degree = sh_degree; a.M = M; a.W = W; a.H = H;
+    a.means3D = g.means3D; a.shs = g.shs; a.colors_precomp = g.colors_precomp; a.scales = g.scales;
+    a.scale_modifier = g.scale_modifier; a.rotations = g.rotations; a.cov3D_precomp = g.cov3D_precomp;
+    a.vw = vw;
+    a.radii = radii; a.geom = geom; a.accum = accum; a.grad_mask = grad_mask;
+    a.dL_dmeans2D = o.means2D; a.dL_dcolors = o.colors; a.dL_dopacity = o.opacity;
+    a.dL_dmeans3D = o.means3D; a.dL_dcov3D = o.cov3D; a.dL_dsh = o.sh; a.dL_dscales = o.scales;
+    a.dL_drotations = o.rotations;
+    for (int v = 0; v < vw.V; v++) {  // gradients of shared Gaussians sum over the views, in view order
+        a.view = v;
+        a.accumulate = v > 0;
+        StageTimer t(GDR_STAGE_GAUSS_BWD, s);
+        GDR_CUDA(gdr::launch_gauss_backward(a, s), "gauss_backward");
+    }
+    return GDR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gdr_forward_project(int P, int sh_degree, int M, int W, int H, const float* means3D, const float* shs,
+                        const float* colors_precomp, const float* opacities, const float* scales,
+                        float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                        const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                        float tan_fovy, int prefiltered, int32_t* radii, void* geom_state, void* image_state,
+                        int32_t* num_rendered_host, int flags, void* stream) {
+    const GaussianInputs g = {means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, scale_modifier};
+    return project_impl("gdr_forward_project", single_view(P, W, H, viewmatrix, projmatrix, campos, nullptr, tan_fovx, tan_fovy),
+                        P, sh_degree, M, W, H, g, prefiltered, radii, geom_state, image_state, num_rendered_host, flags,
+                        (cudaStream_t)stream);
 }
 
 int gdr_forward_render(int P, int W, int H, const float* bg, const int32_t* radii, const void* geom_state,
                        void* image_state, void* splat_stream, void* sort_scratch, int64_t capacity, float* out_color,
                        float* out_depth, float* out_alpha, int flags, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
-    if (P < 0 || W <= 0 || H <= 0 || capacity < 0)
-        return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_forward_render: bad sizes");
-    if (!image_state || !bg || !out_color || !out_depth || !out_alpha)
-        return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_forward_render: a required pointer is NULL");
-    if (capacity > 0 && (!splat_stream || !sort_scratch))
-        return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_forward_render: stream/scratch is NULL with capacity > 0");
-    if (P > 0 && (!geom_state || !radii)) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_forward_render: geom_state is NULL");
-    gdr::ImageState img = gdr::ImageState::carve(image_state, W, H);
-    gdr::Splat* strm = (gdr::Splat*)splat_stream;
-    if (P > 0 && capacity > 0) {
-        gdr::GeomState geom = gdr::GeomState::carve(const_cast<void*>(geom_state), (size_t)P);
-        uint64_t* keys = (uint64_t*)sort_scratch;
-        uint64_t* keys_alt = (uint64_t*)((char*)sort_scratch + gdr::align_up(sizeof(uint64_t) * (size_t)capacity, 256));
-        // the emit cursors are zero here: tile_scan zeroes them and tile_sort re-zeroes them after use
-        {
-            StageTimer t(GDR_STAGE_EMIT, s);
-            GDR_CUDA(gdr::launch_emit(P, W, H, radii, geom, img, keys, capacity, (flags & GDR_FLAG_NO_TILE_CULL) ? 0 : 1, s), "emit");
-        }
-        {
-            StageTimer t(GDR_STAGE_TILE_SORT, s);
-            GDR_CUDA(gdr::launch_tile_sort(W, H, geom, img, keys, keys_alt, strm, capacity, s), "tile_sort");
-        }
-    }
-    {
-        StageTimer t(GDR_STAGE_BLEND_FWD, s);
-        GDR_CUDA(gdr::launch_blend_forward(W, H, bg, img, strm, (P > 0) ? capacity : 0, out_color, out_depth, out_alpha,
-                                           s),
-                 "blend_forward");
-    }
-    return GDR_OK;
+    return render_impl("gdr_forward_render", single_view(P, W, H, nullptr, nullptr, nullptr, bg, 0.f, 0.f), P, W, H, radii,
+                       geom_state, image_state, splat_stream, sort_scratch, capacity, out_color, out_depth, out_alpha,
+                       flags, (cudaStream_t)stream);
 }
 
 int gdr_backward(int P, int sh_degree, int M, int W, int H, const float* bg, const float* means3D, const float* shs,
@@ -200,44 +306,50 @@ int gdr_backward(int P, int sh_degree, int M, int W, int H, const float* bg, con
                  void* backward_scratch, int grad_mask, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
                  float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drotations,
                  void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
-    if (P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_backward: bad sizes");
-    if (P == 0) return GDR_OK;
-    if (!means3D || !radii || !geom_state || !image_state || !out_alpha || !dL_dout_color || !backward_scratch ||
-        !viewmatrix || !projmatrix || !bg)
-        return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_backward: a required pointer is NULL");
-    if (capacity > 0 && !splat_stream) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_backward: splat_stream is NULL");
-    if ((((uintptr_t)backward_scratch) & 15u) || (dL_dmeans2D && (((uintptr_t)dL_dmeans2D) & 15u)) ||
-        (dL_drotations && (((uintptr_t)dL_drotations) & 15u)) || (rotations && (((uintptr_t)rotations) & 15u)))
-        return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_backward: float4 buffers must be 16-byte aligned");
-    gdr::ImageState img = gdr::ImageState::carve(const_cast<void*>(image_state), W, H);
-    gdr::GeomState geom = gdr::GeomState::carve(const_cast<void*>(geom_state), (size_t)P);
-    float* accum = (float*)backward_scratch;
-    GDR_CUDA(cudaMemsetAsync(accum, 0, sizeof(float) * 12 * (size_t)P, s), "memset(accum)");
-    {
-        StageTimer t(GDR_STAGE_BLEND_BWD, s);
-        GDR_CUDA(gdr::launch_blend_backward(W, H, bg, img, (const gdr::Splat*)splat_stream, capacity, out_alpha,
-                                            dL_dout_color, dL_dout_depth, dL_dout_alpha, accum, grad_mask, s),
-                 "blend_backward");
-    }
-    gdr::GaussBackwardArgs a;
-    a.P = P; a.sh_degree = sh_degree; a.M = M; a.W = W; a.H = H;
-    a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.scales = scales;
-    a.scale_modifier = scale_modifier; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
-    a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.campos = campos;
-    a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
-    a.focal_y = H / (2.0f * tan_fovy);
-    a.focal_x = W / (2.0f * tan_fovx);
-    a.radii = radii; a.geom = geom; a.accum = accum; a.grad_mask = grad_mask;
-    a.dL_dmeans2D = dL_dmeans2D; a.dL_dcolors = dL_dcolors; a.dL_dopacity = dL_dopacity;
-    a.dL_dmeans3D = dL_dmeans3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh; a.dL_dscales = dL_dscales;
-    a.dL_drotations = dL_drotations;
-    if (shs && !campos) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_backward: campos is NULL");
-    {
-        StageTimer t(GDR_STAGE_GAUSS_BWD, s);
-        GDR_CUDA(gdr::launch_gauss_backward(a, s), "gauss_backward");
-    }
-    return GDR_OK;
+    const GaussianInputs g = {means3D, shs, colors_precomp, nullptr, scales, rotations, cov3D_precomp, scale_modifier};
+    const GradOutputs o = {dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations};
+    return backward_impl("gdr_backward", single_view(P, W, H, viewmatrix, projmatrix, campos, bg, tan_fovx, tan_fovy), P,
+                         sh_degree, M, W, H, g, radii, geom_state, image_state, splat_stream, capacity, out_alpha,
+                         dL_dout_color, dL_dout_depth, dL_dout_alpha, backward_scratch, grad_mask, o,
+                         (cudaStream_t)stream);
+}
+
+// ---- batched multi-view entry points: V cameras, one set of Gaussians, one launch per stage ----
+int gdr_views_forward_project(int V, int P, int sh_degree, int M, int W, int H, const float* means3D, const float* shs,
+                              const float* colors_precomp, const float* opacities, const float* scales,
+                              float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                              const gdr_camera* cameras, int prefiltered, int32_t* radii, void* geom_states,
+                              void* image_states, int32_t* num_rendered_host, int flags, void* stream) {
+    if (V <= 0 || !cameras) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_views_forward_project: bad V or cameras is NULL");
+    const GaussianInputs g = {means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, scale_modifier};
+    return project_impl("gdr_views_forward_project", batched_views(V, P, W, H, cameras), P, sh_degree, M, W, H, g,
+                        prefiltered, radii, geom_states, image_states, num_rendered_host, flags, (cudaStream_t)stream);
+}
+
+int gdr_views_forward_render(int V, int P, int W, int H, const gdr_camera* cameras, const int32_t* radii,
+                             const void* geom_states, void* image_states, void* splat_streams, void* sort_scratch,
+                             int64_t capacity_per_view, float* out_color, float* out_depth, float* out_alpha, int flags,
+                             void* stream) {
+    if (V <= 0 || !cameras) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_views_forward_render: bad V or cameras is NULL");
+    return render_impl("gdr_views_forward_render", batched_views(V, P, W, H, cameras), P, W, H, radii, geom_states,
+                       image_states, splat_streams, sort_scratch, capacity_per_view, out_color, out_depth, out_alpha,
+                       flags, (cudaStream_t)stream);
+}
+
+int gdr_views_backward(int V, int P, int sh_degree, int M, int W, int H, const float* means3D, const float* shs,
+                       const float* colors_precomp, const float* scales, float scale_modifier, const float* rotations,
+                       const float* cov3D_precomp, const gdr_camera* cameras, const int32_t* radii,
+                       const void* geom_states, const void* image_states, const void* splat_streams,
+                       int64_t capacity_per_view, const float* out_alpha, const float* dL_dout_color,
+                       const float* dL_dout_depth, const float* dL_dout_alpha, void* backward_scratch, int grad_mask,
+                       float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D, float* dL_dcov3D,
+                       float* dL_dsh, float* dL_dscales, float* dL_drotations, void* stream) {
+    if (V <= 0 || !cameras) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_views_backward: bad V or cameras is NULL");
+    const GaussianInputs g = {means3D, shs, colors_precomp, nullptr, scales, rotations, cov3D_precomp, scale_modifier};
+    const GradOutputs o = {dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations};
+    return backward_impl("gdr_views_backward", batched_views(V, P, W, H, cameras), P, sh_degree, M, W, H, g, radii,
+                         geom_states, image_states, splat_streams, capacity_per_view, out_alpha, dL_dout_color,
+                         dL_dout_depth, dL_dout_alpha, backward_scratch, grad_mask, o, (cudaStream_t)stream);
 }
 
 int gdr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,

@@ -31,7 +31,8 @@ namespace {
 
 constexpr int SCAN_THREADS = 1024;
 
-__global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageState img) {
+__global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageState img0, size_t img_stride) {
+    const ImageState img = img0.at(blockIdx.x, img_stride);  // one CTA per view
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t warp_max[32];
     __shared__ uint32_t bucket_count[33];  // tiles per floor(log2(count)) + 1 bucket; bucket 0 = empty tiles
@@ -91,9 +92,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageSta
 constexpr int EMIT_THREADS = 128;
 
 __global__ void __launch_bounds__(EMIT_THREADS)
-emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii, const Splat* __restrict__ splat,
-            const uint32_t* __restrict__ tile_offsets, uint32_t* __restrict__ cursor, uint64_t* __restrict__ keys,
-            uint32_t* __restrict__ header, int64_t capacity, int cull) {
+emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii0, GeomState geom0, ImageState img0,
+            uint64_t* __restrict__ keys0, int64_t capacity, int cull, size_t geom_stride, size_t img_stride) {
+    const int v = blockIdx.y;
+    const int32_t* __restrict__ radii = radii0 + (size_t)v * P;
+    const Splat* __restrict__ splat = geom0.at(v, geom_stride).splat;
+    const ImageState img = img0.at(v, img_stride);
+    const uint32_t* __restrict__ tile_offsets = img.tile_offsets;
+    uint32_t* __restrict__ cursor = img.tile_counter;
+    uint32_t* __restrict__ header = img.header;
+    uint64_t* __restrict__ keys = keys0 + (size_t)v * capacity;
     const int n_vblocks = (P + EMIT_THREADS - 1) / EMIT_THREADS;
     bool overflow = false;
     for (int vb = blockIdx.x; vb < n_vblocks; vb += gridDim.x) {  // virtual blocks: balanced single wave
@@ -176,10 +184,17 @@ __device__ __forceinline__ int lower_bound_u64(const uint64_t* a, int n, uint64_
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
-tile_sort_kernel(const Splat* __restrict__ splat, const uint32_t* __restrict__ tile_offsets,
-                 uint32_t* __restrict__ cursor, uint64_t* keys, uint64_t* keys_alt, Splat* __restrict__ stream,
-                 int64_t capacity) {
+tile_sort_kernel(GeomState geom0, ImageState img0, uint64_t* keys0, uint64_t* keys_alt0, Splat* __restrict__ stream0,
+                 int64_t capacity, size_t geom_stride, size_t img_stride) {
     __shared__ uint64_t s_keys[SORT_CHUNK];
+    const int v = blockIdx.y;
+    const Splat* __restrict__ splat = geom0.at(v, geom_stride).splat;
+    const ImageState img = img0.at(v, img_stride);
+    const uint32_t* __restrict__ tile_offsets = img.tile_offsets;
+    uint32_t* __restrict__ cursor = img.tile_counter;
+    uint64_t* keys = keys0 + (size_t)v * capacity;
+    uint64_t* keys_alt = keys_alt0 + (size_t)v * capacity;
+    Splat* __restrict__ stream = stream0 + (size_t)v * capacity;
     const int tile = blockIdx.x;
     if (threadIdx.x == 0) cursor[tile] = 0;  // leave the bin cursors clean for a (speculative) re-run
     const int64_t b = min((int64_t)tile_offsets[tile], capacity);
@@ -247,29 +262,30 @@ tile_sort_kernel(const Splat* __restrict__ splat, const uint32_t* __restrict__ t
 
 }  // namespace
 
-cudaError_t launch_tile_scan(int T, ImageState img, cudaStream_t s) {
-    tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(T, img);
+cudaError_t launch_tile_scan(int T, ImageState img, const Views& vw, cudaStream_t s) {
+    tile_scan_kernel<<<max(1, vw.V), SCAN_THREADS, 0, s>>>(T, img, vw.img_stride);
     return cudaGetLastError();
 }
 
 cudaError_t launch_emit(int P, int W, int H, const int32_t* radii, GeomState geom, ImageState img, uint64_t* keys,
-                        int64_t capacity, int cull, cudaStream_t s) {
+                        int64_t capacity, int cull, const Views& vw, cudaStream_t s) {
     if (P <= 0) return cudaSuccess;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel, EMIT_THREADS, 0) != cudaSuccess || per_sm < 1)
         per_sm = 1;
-    const int grid = min((P + EMIT_THREADS - 1) / EMIT_THREADS, sm_count() * per_sm);
-    emit_kernel<<<grid, EMIT_THREADS, 0, s>>>(
-        P, gx, gy, radii, geom.splat, img.tile_offsets, img.tile_counter, keys, img.header, capacity, cull);
+    const int V = max(1, vw.V);
+    const int grid = min((P + EMIT_THREADS - 1) / EMIT_THREADS, max(1, sm_count() * per_sm / V));
+    emit_kernel<<<dim3(grid, V), EMIT_THREADS, 0, s>>>(P, gx, gy, radii, geom, img, keys, capacity, cull, vw.geom_stride,
+                                                       vw.img_stride);
     return cudaGetLastError();
 }
 
 cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint64_t* keys, uint64_t* keys_alt,
-                             Splat* stream, int64_t capacity, cudaStream_t s) {
+                             Splat* stream, int64_t capacity, const Views& vw, cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    tile_sort_kernel<<<gx * gy, SORT_THREADS, 0, s>>>(geom.splat, img.tile_offsets, img.tile_counter, keys, keys_alt,
-                                                     stream, capacity);
+    tile_sort_kernel<<<dim3(gx * gy, max(1, vw.V)), SORT_THREADS, 0, s>>>(geom, img, keys, keys_alt, stream, capacity,
+                                                                          vw.geom_stride, vw.img_stride);
     return cudaGetLastError();
 }
 

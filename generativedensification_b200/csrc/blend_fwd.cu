@@ -44,12 +44,23 @@ __device__ __forceinline__ unsigned subblock_mask(float lx, float ly, float4 con
 }
 
 __global__ void __launch_bounds__(BLEND_THREADS)
-blend_forward_kernel(int W, int H, int gx, const float* __restrict__ bg, const uint32_t* __restrict__ tile_offsets, const uint32_t* __restrict__ tile_order,
-                     const Splat* __restrict__ stream, int64_t capacity, uint32_t* __restrict__ n_contrib,
-                     float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha) {
+blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restrict__ stream0, int64_t capacity,
+                     float* __restrict__ out_color0, float* __restrict__ out_depth0, float* __restrict__ out_alpha0,
+                     const Views vw) {
     __shared__ __align__(128) Splat buf[2][CHUNK];
     __shared__ __align__(8) uint64_t full[2];
     __shared__ uint8_t s_mask[CHUNK];
+
+    const int v = blockIdx.y;  // view of the batch
+    const ImageState img = img0.at(v, vw.img_stride);
+    const uint32_t* __restrict__ tile_offsets = img.tile_offsets;
+    const uint32_t* __restrict__ tile_order = img.tile_order;
+    uint32_t* __restrict__ n_contrib = img.n_contrib;
+    const Splat* __restrict__ stream = stream0 + (size_t)v * capacity;
+    const float* __restrict__ bg = vw.bg + (size_t)v * vw.cam_stride;
+    float* __restrict__ out_color = out_color0 + (size_t)v * 3 * H * W;
+    float* __restrict__ out_depth = out_depth0 + (size_t)v * H * W;
+    float* __restrict__ out_alpha = out_alpha0 + (size_t)v * H * W;
 
     const int tile = (int)tile_order[blockIdx.x];  // heaviest tiles first
     const int tile_x = tile % gx, tile_y = tile / gx;
@@ -160,12 +171,12 @@ blend_forward_kernel(int W, int H, int gx, const float* __restrict__ bg, const u
 
 }  // namespace
 
-cudaError_t launch_blend_forward(int W, int H, const float* bg, ImageState img, const Splat* stream,
-                                 int64_t capacity, float* out_color, float* out_depth, float* out_alpha,
+cudaError_t launch_blend_forward(int W, int H, ImageState img, const Splat* stream, int64_t capacity,
+                                 float* out_color, float* out_depth, float* out_alpha, const Views& vw,
                                  cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    blend_forward_kernel<<<gx * gy, BLEND_THREADS, 0, s>>>(W, H, gx, bg, img.tile_offsets, img.tile_order, stream, capacity,
-                                                           img.n_contrib, out_color, out_depth, out_alpha);
+    blend_forward_kernel<<<dim3(gx * gy, max(1, vw.V)), BLEND_THREADS, 0, s>>>(W, H, gx, img, stream, capacity, out_color,
+                                                                               out_depth, out_alpha, vw);
     return cudaGetLastError();
 }
 

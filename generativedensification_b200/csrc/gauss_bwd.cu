@@ -32,33 +32,63 @@ __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y 
 
 constexpr int GB_THREADS = 128;
 
+template <bool ACC>
 __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, const int idx);
 
+// ACC = false stores every requested output row; ACC = true adds to it (views 1.. of a batch launch in
+// stream order after view 0, so the per-Gaussian gradients are summed over views deterministically).
+template <bool ACC>
 __global__ void __launch_bounds__(GB_THREADS) gauss_backward_kernel(const GaussBackwardArgs a) {
     for (int idx = blockIdx.x * GB_THREADS + threadIdx.x; idx < a.P; idx += gridDim.x * GB_THREADS)
-        gauss_backward_one(a, idx);
+        gauss_backward_one<ACC>(a, idx);
 }
 
+template <bool ACC>
+__device__ __forceinline__ void put(float* p, float v) {
+    if (ACC) *p += v; else *p = v;
+}
+template <bool ACC>
+__device__ __forceinline__ void putv(V3* p, V3 v) {
+    if (ACC) {
+        const V3 o = *p;
+        v = V3{o.x + v.x, o.y + v.y, o.z + v.z};
+    }
+    *p = v;
+}
+template <bool ACC>
+__device__ __forceinline__ void put4(float* p, float4 v) {
+    float4* q = reinterpret_cast<float4*>(p);
+    if (ACC) {
+        const float4 o = *q;
+        v = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
+    }
+    *q = v;
+}
+
+template <bool ACC>
 __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, const int idx) {
-    const float4* acc = reinterpret_cast<const float4*>(a.accum + (size_t)idx * 12);
+    const int vi = a.view;
+    const float4* acc = reinterpret_cast<const float4*>(a.accum + ((size_t)vi * a.P + idx) * 12);
     const float4 g_mean2D = acc[0];
     const float4 g_conic_op = acc[1];
     const float4 g_rgb_depth = acc[2];
-    const bool visible = a.radii[idx] > 0;
+    const bool visible = a.radii[(size_t)vi * a.P + idx] > 0;
+    const GeomState geom = a.geom.at(vi, a.vw.geom_stride);
     const int M = a.M;
 
-    if (a.dL_dmeans2D) reinterpret_cast<float4*>(a.dL_dmeans2D)[idx] = g_mean2D;
-    if (a.dL_dopacity) a.dL_dopacity[idx] = g_conic_op.w;
+    if (a.dL_dmeans2D) put4<ACC>(a.dL_dmeans2D + (size_t)idx * 4, g_mean2D);
+    if (a.dL_dopacity) put<ACC>(a.dL_dopacity + idx, g_conic_op.w);
     if (a.dL_dcolors) {
-        a.dL_dcolors[(size_t)idx * 3 + 0] = g_rgb_depth.x;
-        a.dL_dcolors[(size_t)idx * 3 + 1] = g_rgb_depth.y;
-        a.dL_dcolors[(size_t)idx * 3 + 2] = g_rgb_depth.z;
+        put<ACC>(a.dL_dcolors + (size_t)idx * 3 + 0, g_rgb_depth.x);
+        put<ACC>(a.dL_dcolors + (size_t)idx * 3 + 1, g_rgb_depth.y);
+        put<ACC>(a.dL_dcolors + (size_t)idx * 3 + 2, g_rgb_depth.z);
     }
     const bool want_geo = a.dL_dmeans3D || a.dL_dcov3D || a.dL_dscales || a.dL_drotations;
     const bool want_sh = a.dL_dsh != nullptr && a.shs != nullptr;
     if (!want_geo && !want_sh) return;
 
     if (!visible) {
+        if (ACC) return;  // adds nothing
         if (a.dL_dmeans3D)
             for (int k = 0; k < 3; k++) a.dL_dmeans3D[(size_t)idx * 3 + k] = 0.f;
         if (a.dL_dcov3D)
@@ -71,11 +101,14 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
         return;
     }
 
-    const float* view = a.viewmatrix;
-    const float* proj = a.projmatrix;
+    const float* view = a.vw.view + (size_t)vi * a.vw.cam_stride;
+    const float* proj = a.vw.proj + (size_t)vi * a.vw.cam_stride;
+    const float* campos = a.vw.campos + (size_t)vi * a.vw.cam_stride;
+    const float tan_fovx = a.vw.tanx(vi), tan_fovy = a.vw.tany(vi);
+    const float focal_y = a.H / (2.0f * tan_fovy), focal_x = a.W / (2.0f * tan_fovx);
     const float3 mean = make_float3(a.means3D[(size_t)idx * 3], a.means3D[(size_t)idx * 3 + 1],
                                     a.means3D[(size_t)idx * 3 + 2]);
-    const float* cov3D = a.cov3D_precomp ? a.cov3D_precomp + (size_t)idx * 6 : a.geom.cov3D + (size_t)idx * 6;
+    const float* cov3D = a.cov3D_precomp ? a.cov3D_precomp + (size_t)idx * 6 : geom.cov3D + (size_t)idx * 6;
     float dL_dcov[6];
     float3 dL_dmean;
 
@@ -83,13 +116,13 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
     {
         const float3 dL_dconic = make_float3(g_conic_op.x, g_conic_op.y, g_conic_op.z);
         float3 t = xform_point_4x3(mean, view);
-        const float limx = 1.3f * a.tan_fovx, limy = 1.3f * a.tan_fovy;
+        const float limx = 1.3f * tan_fovx, limy = 1.3f * tan_fovy;
         const float txtz = t.x / t.z, tytz = t.y / t.z;
         t.x = min(limx, max(-limx, txtz)) * t.z;
         t.y = min(limy, max(-limy, tytz)) * t.z;
         const float x_grad_mul = txtz < -limx || txtz > limx ? 0.f : 1.f;
         const float y_grad_mul = tytz < -limy || tytz > limy ? 0.f : 1.f;
-        const float h_x = a.focal_x, h_y = a.focal_y;
+        const float h_x = focal_x, h_y = focal_y;
 
         Mat3 J;
         J.m[0][0] = h_x / t.z; J.m[0][1] = 0.0f;      J.m[0][2] = -(h_x * t.x) / (t.z * t.z);
@@ -171,11 +204,11 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
 
     // ---- colour -> SH coefficients and view direction : backward.cu:20-139 ----
     if (a.shs != nullptr) {
-        const V3 dir_orig = {mean.x - a.campos[0], mean.y - a.campos[1], mean.z - a.campos[2]};
+        const V3 dir_orig = {mean.x - campos[0], mean.y - campos[1], mean.z - campos[2]};
         const float len = sqrtf(dot(dir_orig, dir_orig));
         const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
         const V3* sh = reinterpret_cast<const V3*>(a.shs) + (size_t)idx * M;
-        const unsigned cl = a.geom.clamped[idx];
+        const unsigned cl = geom.clamped[idx];
         V3 dRGB = {g_rgb_depth.x, g_rgb_depth.y, g_rgb_depth.z};
         dRGB.x *= (cl & 1u) ? 0.f : 1.f;
         dRGB.y *= (cl & 2u) ? 0.f : 1.f;
@@ -185,14 +218,15 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
         const int deg = a.sh_degree;
         const int used = (deg + 1) * (deg + 1);
         if (dsh) {
-            dsh[0] = kSH0 * dRGB;
-            for (int k = used; k < M; k++) dsh[k] = V3{0.f, 0.f, 0.f};
+            putv<ACC>(dsh + 0, kSH0 * dRGB);
+            if (!ACC)
+                for (int k = used; k < M; k++) dsh[k] = V3{0.f, 0.f, 0.f};
         }
         if (deg > 0) {
             if (dsh) {
-                dsh[1] = (-kSH1 * y) * dRGB;
-                dsh[2] = (kSH1 * z) * dRGB;
-                dsh[3] = (-kSH1 * x) * dRGB;
+                putv<ACC>(dsh + 1, (-kSH1 * y) * dRGB);
+                putv<ACC>(dsh + 2, (kSH1 * z) * dRGB);
+                putv<ACC>(dsh + 3, (-kSH1 * x) * dRGB);
             }
             dRGBdx = -kSH1 * sh[3];
             dRGBdy = -kSH1 * sh[1];
@@ -201,11 +235,11 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
                 const float xx = x * x, yy = y * y, zz = z * z;
                 const float xy = x * y, yz = y * z, xz = x * z;
                 if (dsh) {
-                    dsh[4] = (kSH2[0] * xy) * dRGB;
-                    dsh[5] = (kSH2[1] * yz) * dRGB;
-                    dsh[6] = (kSH2[2] * (2.f * zz - xx - yy)) * dRGB;
-                    dsh[7] = (kSH2[3] * xz) * dRGB;
-                    dsh[8] = (kSH2[4] * (xx - yy)) * dRGB;
+                    putv<ACC>(dsh + 4, (kSH2[0] * xy) * dRGB);
+                    putv<ACC>(dsh + 5, (kSH2[1] * yz) * dRGB);
+                    putv<ACC>(dsh + 6, (kSH2[2] * (2.f * zz - xx - yy)) * dRGB);
+                    putv<ACC>(dsh + 7, (kSH2[3] * xz) * dRGB);
+                    putv<ACC>(dsh + 8, (kSH2[4] * (xx - yy)) * dRGB);
                 }
                 dRGBdx = dRGBdx + (kSH2[0] * y) * sh[4] + (kSH2[2] * 2.f * -x) * sh[6] + (kSH2[3] * z) * sh[7] +
                          (kSH2[4] * 2.f * x) * sh[8];
@@ -214,13 +248,13 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
                 dRGBdz = dRGBdz + (kSH2[1] * y) * sh[5] + (kSH2[2] * 2.f * 2.f * z) * sh[6] + (kSH2[3] * x) * sh[7];
                 if (deg > 2) {
                     if (dsh) {
-                        dsh[9] = (kSH3[0] * y * (3.f * xx - yy)) * dRGB;
-                        dsh[10] = (kSH3[1] * xy * z) * dRGB;
-                        dsh[11] = (kSH3[2] * y * (4.f * zz - xx - yy)) * dRGB;
-                        dsh[12] = (kSH3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * dRGB;
-                        dsh[13] = (kSH3[4] * x * (4.f * zz - xx - yy)) * dRGB;
-                        dsh[14] = (kSH3[5] * z * (xx - yy)) * dRGB;
-                        dsh[15] = (kSH3[6] * x * (xx - 3.f * yy)) * dRGB;
+                        putv<ACC>(dsh + 9, (kSH3[0] * y * (3.f * xx - yy)) * dRGB);
+                        putv<ACC>(dsh + 10, (kSH3[1] * xy * z) * dRGB);
+                        putv<ACC>(dsh + 11, (kSH3[2] * y * (4.f * zz - xx - yy)) * dRGB);
+                        putv<ACC>(dsh + 12, (kSH3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * dRGB);
+                        putv<ACC>(dsh + 13, (kSH3[4] * x * (4.f * zz - xx - yy)) * dRGB);
+                        putv<ACC>(dsh + 14, (kSH3[5] * z * (xx - yy)) * dRGB);
+                        putv<ACC>(dsh + 15, (kSH3[6] * x * (xx - 3.f * yy)) * dRGB);
                     }
                     dRGBdx = dRGBdx + (kSH3[0] * 3.f * 2.f * xy) * sh[9] + (kSH3[1] * yz) * sh[10] +
                              (kSH3[2] * -2.f * xy) * sh[11] + (kSH3[3] * -3.f * 2.f * xz) * sh[12] +
@@ -244,17 +278,17 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
         dL_dmean.x += ((+sum2 - v.x * v.x) * dL_ddir.x - v.y * v.x * dL_ddir.y - v.z * v.x * dL_ddir.z) * invsum32;
         dL_dmean.y += (-v.x * v.y * dL_ddir.x + (sum2 - v.y * v.y) * dL_ddir.y - v.z * v.y * dL_ddir.z) * invsum32;
         dL_dmean.z += (-v.x * v.z * dL_ddir.x - v.y * v.z * dL_ddir.y + (sum2 - v.z * v.z) * dL_ddir.z) * invsum32;
-    } else if (a.dL_dsh) {
+    } else if (a.dL_dsh && !ACC) {
         for (int k = 0; k < 3 * M; k++) a.dL_dsh[(size_t)idx * 3 * M + k] = 0.f;
     }
 
     if (a.dL_dmeans3D) {
-        a.dL_dmeans3D[(size_t)idx * 3 + 0] = dL_dmean.x;
-        a.dL_dmeans3D[(size_t)idx * 3 + 1] = dL_dmean.y;
-        a.dL_dmeans3D[(size_t)idx * 3 + 2] = dL_dmean.z;
+        put<ACC>(a.dL_dmeans3D + (size_t)idx * 3 + 0, dL_dmean.x);
+        put<ACC>(a.dL_dmeans3D + (size_t)idx * 3 + 1, dL_dmean.y);
+        put<ACC>(a.dL_dmeans3D + (size_t)idx * 3 + 2, dL_dmean.z);
     }
     if (a.dL_dcov3D)
-        for (int k = 0; k < 6; k++) a.dL_dcov3D[(size_t)idx * 6 + k] = dL_dcov[k];
+        for (int k = 0; k < 6; k++) put<ACC>(a.dL_dcov3D + (size_t)idx * 6 + k, dL_dcov[k]);
 
     // ---- cov3D -> scale, rotation : backward.cu:278-341 ----
     if (a.scales != nullptr && (a.dL_dscales || a.dL_drotations)) {
@@ -287,9 +321,9 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
         const Mat3 Rt = mat3_transpose(R);
         Mat3 dL_dMt = mat3_transpose(dL_dM);
         if (a.dL_dscales) {
-            a.dL_dscales[(size_t)idx * 3 + 0] = Rt.m[0][0] * dL_dMt.m[0][0] + Rt.m[0][1] * dL_dMt.m[0][1] + Rt.m[0][2] * dL_dMt.m[0][2];
-            a.dL_dscales[(size_t)idx * 3 + 1] = Rt.m[1][0] * dL_dMt.m[1][0] + Rt.m[1][1] * dL_dMt.m[1][1] + Rt.m[1][2] * dL_dMt.m[1][2];
-            a.dL_dscales[(size_t)idx * 3 + 2] = Rt.m[2][0] * dL_dMt.m[2][0] + Rt.m[2][1] * dL_dMt.m[2][1] + Rt.m[2][2] * dL_dMt.m[2][2];
+            put<ACC>(a.dL_dscales + (size_t)idx * 3 + 0, Rt.m[0][0] * dL_dMt.m[0][0] + Rt.m[0][1] * dL_dMt.m[0][1] + Rt.m[0][2] * dL_dMt.m[0][2]);
+            put<ACC>(a.dL_dscales + (size_t)idx * 3 + 1, Rt.m[1][0] * dL_dMt.m[1][0] + Rt.m[1][1] * dL_dMt.m[1][1] + Rt.m[1][2] * dL_dMt.m[1][2]);
+            put<ACC>(a.dL_dscales + (size_t)idx * 3 + 2, Rt.m[2][0] * dL_dMt.m[2][0] + Rt.m[2][1] * dL_dMt.m[2][1] + Rt.m[2][2] * dL_dMt.m[2][2]);
         }
 #pragma unroll
         for (int rr = 0; rr < 3; rr++) {
@@ -303,9 +337,9 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
             dq.y = 2 * y * (dL_dMt.m[1][0] + dL_dMt.m[0][1]) + 2 * z * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) + 2 * r * (dL_dMt.m[1][2] - dL_dMt.m[2][1]) - 4 * x * (dL_dMt.m[2][2] + dL_dMt.m[1][1]);
             dq.z = 2 * x * (dL_dMt.m[1][0] + dL_dMt.m[0][1]) + 2 * r * (dL_dMt.m[2][0] - dL_dMt.m[0][2]) + 2 * z * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * y * (dL_dMt.m[2][2] + dL_dMt.m[0][0]);
             dq.w = 2 * r * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * x * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) + 2 * y * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * z * (dL_dMt.m[1][1] + dL_dMt.m[0][0]);
-            reinterpret_cast<float4*>(a.dL_drotations)[idx] = dq;
+            put4<ACC>(a.dL_drotations + (size_t)idx * 4, dq);
         }
-    } else {
+    } else if (!ACC) {
         if (a.dL_dscales)
             for (int k = 0; k < 3; k++) a.dL_dscales[(size_t)idx * 3 + k] = 0.f;
         if (a.dL_drotations) reinterpret_cast<float4*>(a.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -317,11 +351,15 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
 cudaError_t launch_gauss_backward(const GaussBackwardArgs& a, cudaStream_t s) {
     if (a.P <= 0) return cudaSuccess;
     int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gauss_backward_kernel, GB_THREADS, 0) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gauss_backward_kernel<false>, GB_THREADS, 0) !=
+            cudaSuccess ||
         per_sm < 1)
         per_sm = 1;
     const int grid = min((a.P + GB_THREADS - 1) / GB_THREADS, sm_count() * per_sm);
-    gauss_backward_kernel<<<grid, GB_THREADS, 0, s>>>(a);
+    if (a.accumulate)
+        gauss_backward_kernel<true><<<grid, GB_THREADS, 0, s>>>(a);
+    else
+        gauss_backward_kernel<false><<<grid, GB_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }
 

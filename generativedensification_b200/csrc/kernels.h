@@ -21,13 +21,10 @@ struct ProjectArgs {
     float scale_modifier;
     const float* rotations;
     const float* cov3D_precomp;
-    const float* viewmatrix;
-    const float* projmatrix;
-    const float* campos;
-    float tan_fovx, tan_fovy, focal_x, focal_y;
     int prefiltered;
     int cull;  // exact tile-level culling of (Gaussian, tile) pairs that cannot reach alpha = 1/255
-    int32_t* radii;
+    Views vw;          // cameras + per-view strides; every per-view pointer below is view 0's
+    int32_t* radii;    // [V][P]
     GeomState geom;
     ImageState img;
 };
@@ -38,21 +35,23 @@ cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewma
                                 cudaStream_t s);
 
 // binning.cu: tile scan, instance emission, per-tile depth sort + record gather
-cudaError_t launch_tile_scan(int T, ImageState img, cudaStream_t s);
+// Batched layout (V = vw.V views, blockIdx.y = view): keys / keys_alt / stream hold `capacity` entries per
+// view back to back; images are [V][C][H][W]; radii [V][P]; accum [V][P][12].
+cudaError_t launch_tile_scan(int T, ImageState img, const Views& vw, cudaStream_t s);
 cudaError_t launch_emit(int P, int W, int H, const int32_t* radii, GeomState geom, ImageState img, uint64_t* keys,
-                        int64_t capacity, int cull, cudaStream_t s);
+                        int64_t capacity, int cull, const Views& vw, cudaStream_t s);
 cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint64_t* keys, uint64_t* keys_alt,
-                             Splat* stream, int64_t capacity, cudaStream_t s);
+                             Splat* stream, int64_t capacity, const Views& vw, cudaStream_t s);
 
 // blend_fwd.cu
-cudaError_t launch_blend_forward(int W, int H, const float* bg, ImageState img, const Splat* stream,
-                                 int64_t capacity, float* out_color, float* out_depth, float* out_alpha,
+cudaError_t launch_blend_forward(int W, int H, ImageState img, const Splat* stream, int64_t capacity,
+                                 float* out_color, float* out_depth, float* out_alpha, const Views& vw,
                                  cudaStream_t s);
 
-// blend_bwd.cu: accum is [P][12] floats: (mean2D x,y,|x|,|y|), (conic a,b,c, opacity), (r,g,b, depth)
-cudaError_t launch_blend_backward(int W, int H, const float* bg, ImageState img, const Splat* stream,
-                                  int64_t capacity, const float* out_alpha, const float* dL_dcolor,
-                                  const float* dL_ddepth, const float* dL_dalpha, float* accum, int grad_mask,
+// blend_bwd.cu: accum is [V][P][12] floats: (mean2D x,y,|x|,|y|), (conic a,b,c, opacity), (r,g,b, depth)
+cudaError_t launch_blend_backward(int P, int W, int H, ImageState img, const Splat* stream, int64_t capacity,
+                                  const float* out_alpha, const float* dL_dcolor, const float* dL_ddepth,
+                                  const float* dL_dalpha, float* accum, int grad_mask, const Views& vw,
                                   cudaStream_t s);
 
 struct GaussBackwardArgs {
@@ -64,13 +63,12 @@ struct GaussBackwardArgs {
     float scale_modifier;
     const float* rotations;
     const float* cov3D_precomp;
-    const float* viewmatrix;
-    const float* projmatrix;
-    const float* campos;
-    float tan_fovx, tan_fovy, focal_x, focal_y;
-    const int32_t* radii;
+    Views vw;
+    int view;          // which view of the batch this launch handles (its state is found through vw)
+    int accumulate;    // 0: store the outputs; 1: add to them (views 1.. of a batch: gradients sum over views)
+    const int32_t* radii;  // [V][P]
     GeomState geom;
-    const float* accum;
+    const float* accum;    // [V][P][12]
     int grad_mask;
     float* dL_dmeans2D;
     float* dL_dcolors;

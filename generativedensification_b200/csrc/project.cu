@@ -153,6 +153,15 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, float3 pos, float3 campos, 
 
 __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs a) {
     extern __shared__ __align__(16) float smem[];
+    const int v = blockIdx.y;  // view of the batch
+    const float* __restrict__ viewmatrix = a.vw.view + (size_t)v * a.vw.cam_stride;
+    const float* __restrict__ projmatrix = a.vw.proj + (size_t)v * a.vw.cam_stride;
+    const float tan_fovx = a.vw.tanx(v), tan_fovy = a.vw.tany(v);
+    const float focal_y = a.H / (2.0f * tan_fovy);  // rasterizer_impl.cu:222-223
+    const float focal_x = a.W / (2.0f * tan_fovx);
+    const GeomState geom = a.geom.at(v, a.vw.geom_stride);
+    const ImageState img = a.img.at(v, a.vw.img_stride);
+    int32_t* __restrict__ radii = a.radii + (size_t)v * a.P;
     const int n_vblocks = (a.P + PROJ_THREADS - 1) / PROJ_THREADS;
     for (int vb = blockIdx.x; vb < n_vblocks; vb += gridDim.x) {  // virtual blocks: balanced single wave
     if (vb != (int)blockIdx.x) __syncthreads();                  // the staging buffers are reused
@@ -184,10 +193,10 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
 
         const float3 p_orig = make_float3(s_mean[3 * threadIdx.x], s_mean[3 * threadIdx.x + 1],
                                           s_mean[3 * threadIdx.x + 2]);
-        const float4 p_hom = xform_point_4x4(p_orig, a.projmatrix);
+        const float4 p_hom = xform_point_4x4(p_orig, projmatrix);
         const float p_w = 1.0f / (p_hom.w + 0.0000001f);
         const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
-        const float3 p_view = xform_point_4x3(p_orig, a.viewmatrix);
+        const float3 p_view = xform_point_4x3(p_orig, viewmatrix);
 
         if (p_view.z > NEAR_Z) {  // near-plane cull only (auxiliary.h:152)
             if (a.cov3D_precomp != nullptr) {
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
                 const float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
                 cov3d_from_scale_rot(sc, a.scale_modifier, q, cov3D);
             }
-            const float3 cov = cov2d_ewa(p_orig, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, cov3D, a.viewmatrix);
+            const float3 cov = cov2d_ewa(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov3D, viewmatrix);
             const float det = (cov.x * cov.z - cov.y * cov.y);
             if (det != 0.0f) {
                 const float det_inv = 1.f / det;
@@ -214,7 +223,8 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
                 if ((x1 - x0) * (y1 - y0) != 0) {
                     float3 rgb;
                     if (use_sh) {
-                        const float3 cam = make_float3(__ldg(a.campos), __ldg(a.campos + 1), __ldg(a.campos + 2));
+                        const float* cp = a.vw.campos + (size_t)v * a.vw.cam_stride;
+                        const float3 cam = make_float3(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2));
                         rgb = sh_to_rgb(a.sh_degree, p_orig, cam, s_sh + (size_t)threadIdx.x * 3 * a.M, clamp_bits);
                     } else {
                         rgb = make_float3(__ldg(a.colors_precomp + (size_t)idx * 3),
@@ -238,14 +248,14 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
                 }
             }
         } else if (a.prefiltered) {
-            atomicOr(&a.img.header[HDR_OVERFLOW], 2u);  // reference traps here (auxiliary.h:154-158); we flag
+            atomicOr(&img.header[HDR_OVERFLOW], 2u);  // reference traps here (auxiliary.h:154-158); we flag
         }
-        a.radii[idx] = radius_out;
-        a.geom.splat[idx] = rec;
-        a.geom.tiles_touched[idx] = (uint32_t)n_tiles;
-        a.geom.clamped[idx] = (uint8_t)clamp_bits;
+        radii[idx] = radius_out;
+        geom.splat[idx] = rec;
+        geom.tiles_touched[idx] = (uint32_t)n_tiles;
+        geom.clamped[idx] = (uint8_t)clamp_bits;
         if (a.cov3D_precomp == nullptr) {
-            float2* c = reinterpret_cast<float2*>(a.geom.cov3D + (size_t)idx * 6);
+            float2* c = reinterpret_cast<float2*>(geom.cov3D + (size_t)idx * 6);
             c[0] = make_float2(cov3D[0], cov3D[1]);
             c[1] = make_float2(cov3D[2], cov3D[3]);
             c[2] = make_float2(cov3D[4], cov3D[5]);
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
     // ---- bin counters: one aggregated atomic per distinct tile per warp step ----
     // With culling on, a (Gaussian, tile) pair is only counted if the splat can reach alpha >= 1/255
     // somewhere in the tile (exact: see splat_misses_rect); emit_kernel applies the identical test.
-    uint32_t* counter = a.img.tile_counter;
+    uint32_t* counter = img.tile_counter;
     const bool cull = a.cull != 0;
     const int gx = a.gx;
     warp_foreach_tile(n_tiles, rx0, ry0, rw, gx, [&](int tile, int owner, int, bool valid, unsigned) {
@@ -310,8 +320,9 @@ cudaError_t launch_project(const ProjectArgs& a, cudaStream_t s) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, project_kernel, PROJ_THREADS, smem) != cudaSuccess ||
         per_sm < 1)
         per_sm = 1;
-    const int grid = min(n_vblocks, sm_count() * per_sm);
-    project_kernel<<<grid, PROJ_THREADS, smem, s>>>(a);
+    const int V = max(1, a.vw.V);
+    const int grid = min(n_vblocks, max(1, sm_count() * per_sm / V));  // one balanced wave over all views
+    project_kernel<<<dim3(grid, V), PROJ_THREADS, smem, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -48,6 +48,16 @@ struct GeomState {
         g.clamped = (uint8_t*)(p + o);
         return g;
     }
+    // the same state of view v of a batch whose per-view states are `stride` bytes apart
+    __host__ __device__ GeomState at(int v, size_t stride) const {
+        GeomState g;
+        const size_t off = (size_t)v * stride;
+        g.splat = (Splat*)((char*)splat + off);
+        g.cov3D = (float*)((char*)cov3D + off);
+        g.tiles_touched = (uint32_t*)((char*)tiles_touched + off);
+        g.clamped = clamped + off;
+        return g;
+    }
 };
 
 constexpr int IMG_HEADER_WORDS = 64;
@@ -87,6 +97,35 @@ struct ImageState {
         s.n_contrib = (uint32_t*)(p + o);
         return s;
     }
+    __host__ __device__ ImageState at(int v, size_t stride) const {
+        ImageState s;
+        const size_t off = (size_t)v * stride;
+        s.header = (uint32_t*)((char*)header + off);
+        s.tile_offsets = (uint32_t*)((char*)tile_offsets + off);
+        s.tile_counter = (uint32_t*)((char*)tile_counter + off);
+        s.tile_order = (uint32_t*)((char*)tile_order + off);
+        s.n_contrib = (uint32_t*)((char*)n_contrib + off);
+        return s;
+    }
+};
+
+// How a kernel finds view v = blockIdx.y of a batch of V views that share one set of Gaussians.
+// The single-view entry points use V = 1 with every stride 0 and the tangents passed by value; the
+// batched entry points point view/proj/campos/bg/tanfov into an array of gdr_camera blocks
+// (include/gdr.h) with cam_stride = 48 floats.
+struct Views {
+    int V;
+    size_t geom_stride;  // bytes between consecutive views' GeomState
+    size_t img_stride;   // bytes between consecutive views' ImageState
+    size_t cam_stride;   // floats between consecutive views' camera parameters
+    const float* view;   // [16] transposed world->view matrix of view 0
+    const float* proj;   // [16] transposed full projection of view 0
+    const float* campos; // [3]
+    const float* bg;     // [3]
+    const float* tanfov; // {tan_fovx, tan_fovy} of view 0 in device memory, or nullptr: use the two fields below
+    float tan_fovx, tan_fovy;
+    __device__ __forceinline__ float tanx(int v) const { return tanfov ? __ldg(tanfov + v * cam_stride) : tan_fovx; }
+    __device__ __forceinline__ float tany(int v) const { return tanfov ? __ldg(tanfov + v * cam_stride + 1) : tan_fovy; }
 };
 
 }  // namespace gdr

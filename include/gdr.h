@@ -125,6 +125,52 @@ GDR_API int gdr_backward(int P, int sh_degree, int M, int W, int H, const float*
 GDR_API int gdr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      uint8_t* present, void* stream);
 
+/* ---- Batched multi-view entry points -------------------------------------------------
+ * One set of Gaussians rendered from V cameras with ONE launch per stage (grid.y = view) instead of V
+ * passes through the single-view entry points -- the shape of the reference's per-view loops
+ * (lightning/network.py:827-838, 848-856, 964-972: `for j, c2w in enumerate(tar_c2ws)` around
+ * Renderer.render_img, lightning/renderer.py:209-272).  Cameras live in DEVICE memory as an array of
+ * gdr_camera blocks (what MiniCam, lightning/utils.py:22-48, plus Renderer.set_rasterizer,
+ * renderer.py:106-126, hand to the rasterizer per view).  All V views share W, H, sh_degree and
+ * scale_modifier.  Per-view buffers are the single-view buffers repeated V times back to back:
+ *     radii [V][P];  geom_states V * gdr_geom_state_bytes(P);  image_states V * gdr_image_state_bytes(W,H);
+ *     splat_streams gdr_splat_stream_bytes(V * capacity_per_view)  (view v starts at record v * capacity);
+ *     sort_scratch  gdr_sort_scratch_bytes(V * capacity_per_view);
+ *     images [V][3|1][H][W];  num_rendered_host [V] (pinned);  backward_scratch gdr_backward_scratch_bytes(V * P).
+ * gdr_views_backward SUMS the gradients of the shared Gaussians over the views (what autograd does when
+ * the reference renders the views one by one from the same tensors), deterministically in view order. */
+typedef struct gdr_camera {
+    float viewmatrix[16]; /* transposed world->view (MiniCam.world_view_transform) */
+    float projmatrix[16]; /* transposed full projection (MiniCam.full_proj_transform) */
+    float campos[3];      /* MiniCam.camera_center */
+    float tan_fovx, tan_fovy;
+    float bg[3];
+    float reserved[8];
+} gdr_camera; /* 48 floats */
+#define GDR_CAMERA_FLOATS 48
+
+GDR_API int gdr_views_forward_project(int V, int P, int sh_degree, int M, int W, int H,
+                        const float* means3D, const float* shs, const float* colors_precomp,
+                        const float* opacities, const float* scales, float scale_modifier,
+                        const float* rotations, const float* cov3D_precomp,
+                        const gdr_camera* cameras /* device [V] */, int prefiltered,
+                        int32_t* radii /* out [V][P] */, void* geom_states, void* image_states,
+                        int32_t* num_rendered_host /* pinned [V] or NULL */, int flags, void* stream);
+GDR_API int gdr_views_forward_render(int V, int P, int W, int H, const gdr_camera* cameras, const int32_t* radii,
+                        const void* geom_states, void* image_states, void* splat_streams, void* sort_scratch,
+                        int64_t capacity_per_view, float* out_color /*[V,3,H,W]*/, float* out_depth /*[V,1,H,W]*/,
+                        float* out_alpha /*[V,1,H,W]*/, int flags, void* stream);
+GDR_API int gdr_views_backward(int V, int P, int sh_degree, int M, int W, int H,
+                        const float* means3D, const float* shs, const float* colors_precomp,
+                        const float* scales, float scale_modifier, const float* rotations,
+                        const float* cov3D_precomp, const gdr_camera* cameras, const int32_t* radii,
+                        const void* geom_states, const void* image_states, const void* splat_streams,
+                        int64_t capacity_per_view, const float* out_alpha /*[V,1,H,W]*/,
+                        const float* dL_dout_color /*[V,3,H,W]*/, const float* dL_dout_depth /* or NULL */,
+                        const float* dL_dout_alpha /* or NULL */, void* backward_scratch, int grad_mask,
+                        float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
+                        float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drotations, void* stream);
+
 /* Introspection for tests: copies of the per-Gaussian state in the reference's field layout
  * (geomState.means2D / depths / conic_opacity / rgb / tiles_touched / clamped, rasterizer_impl.h:33-48).
  * Any output pointer may be NULL. */
