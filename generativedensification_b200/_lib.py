@@ -41,6 +41,9 @@ SIGNATURES = {
     "gdr_views_forward_render": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
     "gdr_views_backward": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
                                 _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gdr_mse_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "gdr_views_densify_scores": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gdr_topk_select": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "gdr_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "gdr_debug_unpack_geom": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gdr_debug_unpack_bins": (_i, [_i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),

@@ -352,6 +352,50 @@ int gdr_views_backward(int V, int P, int sh_degree, int M, int W, int H, const f
                          dL_dout_depth, dL_dout_alpha, backward_scratch, grad_mask, o, (cudaStream_t)stream);
 }
 
+// ---- the densify select, fused on the device ----
+int gdr_mse_grad(int V, int W, int H, const float* color, const float* target, float* dL_dcolor, float* loss,
+                 void* stream) {
+    if (V <= 0 || W <= 0 || H <= 0 || !color || !target || !dL_dcolor)
+        return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_mse_grad: bad arguments");
+    GDR_CUDA(gdr::launch_mse_grad(V, W, H, color, target, dL_dcolor, loss, (cudaStream_t)stream), "mse_grad");
+    return GDR_OK;
+}
+
+int gdr_views_densify_scores(int V, int P, int W, int H, const gdr_camera* cameras, const void* image_states,
+                             const void* splat_streams, int64_t capacity_per_view, const float* out_alpha,
+                             const float* dL_dout_color, void* backward_scratch, const uint8_t* candidate_mask,
+                             float* grad_means2D, float* scores, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (V <= 0 || P < 0 || W <= 0 || H <= 0 || capacity_per_view < 0 || !cameras)
+        return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_views_densify_scores: bad sizes or cameras is NULL");
+    if (P == 0) return GDR_OK;
+    if (!image_states || !out_alpha || !dL_dout_color || !backward_scratch || !scores ||
+        (capacity_per_view > 0 && !splat_streams))
+        return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_views_densify_scores: a required pointer is NULL");
+    if ((((uintptr_t)backward_scratch) & 15u) || (grad_means2D && (((uintptr_t)grad_means2D) & 15u)))
+        return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_views_densify_scores: float4 buffers must be 16-byte aligned");
+    const gdr::Views vw = batched_views(V, P, W, H, cameras);
+    gdr::ImageState img = gdr::ImageState::carve(const_cast<void*>(image_states), W, H);
+    float* accum = (float*)backward_scratch;
+    GDR_CUDA(cudaMemsetAsync(accum, 0, sizeof(float) * 12 * (size_t)P * (size_t)V, s), "memset(accum)");
+    {
+        StageTimer t(GDR_STAGE_BLEND_BWD, s);
+        GDR_CUDA(gdr::launch_blend_backward(P, W, H, img, (const gdr::Splat*)splat_streams, capacity_per_view, out_alpha,
+                                            dL_dout_color, nullptr, nullptr, accum, GDR_GRAD_MEANS2D, vw, s),
+                 "blend_backward");
+    }
+    GDR_CUDA(gdr::launch_densify_score(V, P, accum, candidate_mask, grad_means2D, scores, s), "densify_score");
+    return GDR_OK;
+}
+
+int gdr_topk_select(int P, const float* scores, int k, uint8_t* selected, int32_t* selected_idx, int32_t* rest_idx,
+                    int32_t* counts, void* stream) {
+    if (P < 0 || (P > 0 && !scores)) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_topk_select: bad arguments");
+    GDR_CUDA(gdr::launch_topk_select(P, scores, k, selected, selected_idx, rest_idx, counts, (cudaStream_t)stream),
+             "topk_select");
+    return GDR_OK;
+}
+
 int gdr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
                      void* stream) {
     (void)projmatrix;  // the reference's test only uses the view-space depth (auxiliary.h:152)

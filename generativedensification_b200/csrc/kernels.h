@@ -82,6 +82,14 @@ struct GaussBackwardArgs {
 // gauss_bwd.cu: fused per-Gaussian chain rule (conic -> cov2D -> cov3D -> scale/rot, mean2D/depth -> mean3D, SH)
 cudaError_t launch_gauss_backward(const GaussBackwardArgs& a, cudaStream_t s);
 
+// densify.cu: the densify select either side of the raster path (lightning/network.py:865-893)
+cudaError_t launch_mse_grad(int V, int W, int H, const float* color, const float* target, float* dL_dcolor,
+                            float* loss, cudaStream_t s);
+cudaError_t launch_densify_score(int V, int P, const float* accum, const uint8_t* candidate, float* grad, float* score,
+                                 cudaStream_t s);
+cudaError_t launch_topk_select(int P, const float* score, int k, uint8_t* selected, int32_t* selected_idx,
+                               int32_t* rest_idx, int32_t* counts, cudaStream_t s);
+
 // debug.cu
 cudaError_t launch_unpack_geom(int P, GeomState geom, float* means2D, float* depths, float* conic_opacity, float* rgb,
                                float* cov3D, uint32_t* tiles_touched, uint8_t* clamped, cudaStream_t s);

@@ -171,6 +171,29 @@ GDR_API int gdr_views_backward(int V, int P, int sh_degree, int M, int W, int H,
                         float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
                         float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drotations, void* stream);
 
+/* ---- The densify select either side of the path, fused on the device -----------------
+ * Reference: lightning/network.py:865-893 -- vjp of the image MSE through the n_views_sel-view render
+ * w.r.t. ONE shared [P,4] screen-space tensor, then grad[mask][:, 2:4].norm(dim=-1) -> torch.topk(k_num) ->
+ * boolean mask, followed by boolean-mask gathers of the selected / non-selected sets (:905-915, 955-959).
+ *   gdr_mse_grad              dL/dcolor [V,3,H,W] of mean((clamp(color,0,1) - target)^2), target [V,H,W,3]
+ *                             (renderer.py:261 clamp + network.py:855-862 loss); *loss (device, may be NULL).
+ *   gdr_views_densify_scores  means2D-only backward blend of all V views, summed over the views:
+ *                             grad_means2D [P,4] (may be NULL) and scores [P] = ||grad[:,2:4]||, or -1 where
+ *                             candidate_mask[i] == 0 (candidate_mask NULL = every Gaussian is a candidate).
+ *   gdr_topk_select           selected[i] = 1 for the k candidates with the largest scores (all candidates if
+ *                             there are fewer than k; ties at the threshold go to the lowest indices), plus
+ *                             selected_idx / rest_idx (ascending Gaussian indices of the selected / the
+ *                             non-selected candidates) and counts[2] = their lengths -- all device memory,
+ *                             any output may be NULL; exact radix select, no sort, no host round trip. */
+GDR_API int gdr_mse_grad(int V, int W, int H, const float* color, const float* target, float* dL_dcolor, float* loss,
+                        void* stream);
+GDR_API int gdr_views_densify_scores(int V, int P, int W, int H, const gdr_camera* cameras, const void* image_states,
+                        const void* splat_streams, int64_t capacity_per_view, const float* out_alpha,
+                        const float* dL_dout_color, void* backward_scratch /* gdr_backward_scratch_bytes(V*P) */,
+                        const uint8_t* candidate_mask, float* grad_means2D, float* scores, void* stream);
+GDR_API int gdr_topk_select(int P, const float* scores, int k, uint8_t* selected, int32_t* selected_idx,
+                        int32_t* rest_idx, int32_t* counts, void* stream);
+
 /* Introspection for tests: copies of the per-Gaussian state in the reference's field layout
  * (geomState.means2D / depths / conic_opacity / rgb / tiles_touched / clamped, rasterizer_impl.h:33-48).
  * Any output pointer may be NULL. */
