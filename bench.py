@@ -155,6 +155,35 @@ def build_step(mod, device, cams, up_dev, a):
     return step
 
 
+def build_batched_step(device, cams, up_dev, a):
+    """The same step through the opt-in batched entry point: ONE call renders and back-propagates all views."""
+    from generativedensification_b200 import synthetic as S
+    from generativedensification_b200.views import CameraBatch, MultiViewRasterizer
+
+    cb = CameraBatch.from_settings([S.settings_for(cam, torch.ones(3), SH_DEGREE, device) for cam in cams])
+    rast = MultiViewRasterizer(cb)
+    V = len(cams)
+    Gc, Gd, Ga = (u.unsqueeze(0).expand(V, *u.shape).contiguous() for u in up_dev)
+
+    def step(gd):
+        leaves = [gd["means3D"], gd["shs"], gd["opacities"], gd["scales"], gd["rotations"]]
+        m2 = torch.zeros(gd["means3D"].shape[0], 4, device=device, requires_grad=True)
+        color, radii, depth, alpha = rast(means3D=gd["means3D"], means2D=m2, opacities=gd["opacities"], shs=gd["shs"],
+                                          scales=gd["scales"], rotations=gd["rotations"])
+        return torch.autograd.grad([color, depth, alpha], [m2] + leaves, [Gc, Gd, Ga])
+
+    return step
+
+
+def measured_traffic(kernel: str):
+    """dram bytes (read + write) per launch of `kernel` from the committed ncu --set full capture, or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return float(json.load(open(path))[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def time_steps(step_fn, steps, warmup, device, flush):
     """CUDA-event time of `steps` calls (L2 flushed between steps, outside the timed brackets). Returns total ms."""
     for _ in range(warmup):
@@ -286,6 +315,13 @@ def main():
     shard.barrier()
     e2e_ms = shard.max_over_ranks(e2e_ms, device)
 
+    # the same step through the batched entry point (opt-in API; reported beside the drop-in numbers)
+    bstep = build_batched_step(device, cams, up_dev, a)
+    shard.barrier()
+    batched_ms = time_steps(lambda: bstep(gd), a.steps, max(3, a.warmup // 2), device, flush)
+    shard.barrier()
+    batched_ms = shard.max_over_ranks(batched_ms, device)
+
     # per-stage device time of our kernels (same steps, events around every launch)
     _lib.profile_enable(True)
     _lib.profile_read()
@@ -299,17 +335,29 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
-        # instance count of this workload (per view), read back from the library's own state
-        Rs = []
-        with torch.no_grad():
-            for cam in cams:
-                from generativedensification_b200 import synthetic as S
-                settings = S.settings_for(cam, torch.ones(3), SH_DEGREE, device)
-                *_, st = ours._forward_impl(settings, gd["means3D"].detach(), gd["shs"].detach(), torch.Tensor([]),
-                                            gd["opacities"].detach(), gd["scales"].detach(),
-                                            gd["rotations"].detach(), torch.Tensor([]))
-                Rs.append(st.num_rendered)
-        R = sum(Rs) / len(Rs)
+        # instance counts of this workload (per view), read back from the library's own state: R = the
+        # reference's num_rendered (every tile of the 3-sigma rectangle; what SURVEY.md 8d's algorithmic bytes
+        # are defined on), R_culled = what our binning actually emits after exact tile culling
+        from generativedensification_b200 import synthetic as S
+
+        def count_instances(tile_cull):
+            old = ours.options["tile_cull"]
+            ours.options["tile_cull"] = tile_cull
+            try:
+                out = []
+                with torch.no_grad():
+                    for cam in cams:
+                        settings = S.settings_for(cam, torch.ones(3), SH_DEGREE, device)
+                        *_, st = ours._forward_impl(settings, gd["means3D"].detach(), gd["shs"].detach(),
+                                                    torch.Tensor([]), gd["opacities"].detach(), gd["scales"].detach(),
+                                                    gd["rotations"].detach(), torch.Tensor([]))
+                        out.append(st.num_rendered)
+                return sum(out) / len(out)
+            finally:
+                ours.options["tile_cull"] = old
+
+        R = count_instances(False)
+        R_culled = count_instances(True)
         P, HW, M = a.gaussians, a.res * a.res, (SH_DEGREE + 1) ** 2
         per_stage = {k: (ms / max(n, 1)) for k, (ms, n) in stages.items()}
         share = {k: ms for k, (ms, n) in stages.items()}
@@ -334,14 +382,18 @@ def main():
                          "ms_per_step": e2e_ms / a.steps},
                     gpu_launches=7 * a.views * a.steps,
                     roofline={"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                              "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                              "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": measured_traffic(dominant),
                               "peak_source": f"of {peak_kind}", "ms_per_launch": dom_ms,
                               "algorithmic_bytes_per_launch": alg[dominant],
                               "note": "blend kernels are FP32-issue/atomic bound, not HBM bound (SURVEY 7.3.1)"},
                     pipeline={"algorithmic_bytes_per_view": B_f + B_b, "achieved": pipe_achieved, "unit": "GB/s",
                               "frac_of_hbm_peak": pipe_achieved / hbm_peak, "instances_per_view": R,
+                              "instances_per_view_after_culling": R_culled,
                               "pair_evals_per_view": pairs_per_view,
                               "pair_evals_per_s": pairs_per_view * 2 * views_per_s / a.gpus},
+                    batched={"value": a.views * a.gpus * a.steps / (batched_ms * 1e-3), "unit": "views/s",
+                             "ms_per_step": batched_ms / a.steps,
+                             "api": "MultiViewRasterizer: one launch per stage for all views (opt-in; SURVEY 8f-1)"},
                     stage_ms_per_launch={k: round(v, 5) for k, v in per_stage.items()}, stage_share=share,
                     clocks=clocks)
         if a.gpus == 1 and not a.no_cpu_baseline:

@@ -12,12 +12,17 @@
 //     per-thread loads and re-reads colour and depth from global memory for
 //     every contributing (pixel, Gaussian) pair;
 //   * the kernel is instruction-issue bound (ncu: ~90 % issue-slot utilisation), so
-//     the lever is fewer (pixel, splat) evaluations.  A warp owns an 8x4 pixel
-//     block; after a chunk lands, each thread classifies ONE record against the
-//     eight 8x4 blocks of the tile with the exact rectangle bound of common.cuh
-//     (an 8-bit mask), and every warp then walks only the records whose bit is set
-//     for its block (ballot + find-first-set).  Records that cannot reach
-//     alpha = 1/255 anywhere in a warp's block cost that warp nothing;
+//     the levers are fewer (pixel, splat) evaluations and fewer issue slots per
+//     evaluation.  A warp owns an 8x8 pixel region, each lane TWO pixels (rows y and
+//     y + 4) whose values travel as packed FP32 pairs: the exponent, the exp range
+//     reduction and the blend are FFMA2 / FMUL2 / FADD2 (sm_100 packed FP32, the same
+//     IEEE roundings as the scalar code, one issue slot for both pixels), and the
+//     list walk, the shared-memory loads and the votes are paid once per two pixels.
+//     After a chunk lands, the threads classify its records against the four 8x8
+//     regions of the tile with the exact rectangle bound of common.cuh (a 4-bit
+//     mask), and every warp walks only the records whose bit is set for its region
+//     (ballot + find-first-set).  Records that cannot reach alpha = 1/255 anywhere
+//     in a warp's region cost that warp nothing;
 //   * for the pairs that are evaluated, a per-record conservative threshold on the
 //     exponent skips the expf when alpha cannot reach 1/255 (exact: the slack is far
 //     larger than any rounding error; everything near the cut takes the reference's
@@ -28,17 +33,17 @@ namespace gdr {
 
 namespace {
 
-constexpr int BLEND_THREADS = 256;
+constexpr int BLEND_THREADS = 128;  // 4 warps, each owns an 8x8 pixel region: 2 pixels (rows y and y+4) per lane
 constexpr int CHUNK = 256;
 
-// Bit w of the result is set iff the record may contribute to the 8x4 pixel block of warp w.
+// Bit w of the result is set iff the record may contribute to the 8x8 pixel region of warp w.
 // (lx, ly) = splat centre relative to the tile's first pixel.
-__device__ __forceinline__ unsigned subblock_mask(float lx, float ly, float4 con_o, float thr) {
+__device__ __forceinline__ unsigned region_mask(float lx, float ly, float4 con_o, float thr) {
     unsigned m = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-        const float x0 = (float)((w & 1) * 8), y0 = (float)((w >> 1) * 4);
-        if (!splat_misses_rect(lx, ly, con_o.x, con_o.y, con_o.z, thr, x0, y0, x0 + 7.f, y0 + 3.f)) m |= 1u << w;
+    for (int w = 0; w < 4; w++) {
+        const float x0 = (float)((w & 1) * 8), y0 = (float)((w >> 1) * 8);
+        if (!splat_misses_rect(lx, ly, con_o.x, con_o.y, con_o.z, thr, x0, y0, x0 + 7.f, y0 + 7.f)) m |= 1u << w;
     }
     return m;
 }
@@ -72,9 +77,10 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = tile_x * TILE + (warp & 1) * 8 + (lane & 7);
-    const int py = tile_y * TILE + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = px < W && py < H;
-    const float2 pixf = make_float2((float)px, (float)py);
+    const int pya = tile_y * TILE + (warp >> 1) * 8 + (lane >> 3), pyb = pya + 4;
+    const bool inside_a = px < W && pya < H, inside_b = px < W && pyb < H;
+    const float pxf = (float)px;
+    const f32x2 pyf2 = pk((float)pya, (float)pyb);
     const float tile_fx = (float)(tile_x * TILE), tile_fy = (float)(tile_y * TILE);
 
     if (threadIdx.x == 0) {
@@ -89,10 +95,13 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
         bulk_g2s(&buf[0][0], src, bytes, &full[0]);
     }
 
-    bool done = !inside;
-    float T = 1.0f;
-    float C0 = 0.f, C1 = 0.f, C2 = 0.f, weight = 0.f, D = 0.f;
-    uint32_t last_contributor = 0;
+    bool done_a = !inside_a, done_b = !inside_b;
+    f32x2 T2 = pk2(1.0f);
+    // (the colour / depth sums stay scalar: ptxas will not accumulate an FFMA2 in place when its product
+    // operand dies, and the register copies that follow cost more issue slots than the packing saves)
+    float C0a = 0.f, C0b = 0.f, C1a = 0.f, C1b = 0.f, C2a = 0.f, C2b = 0.f, Da = 0.f, Db = 0.f;
+    f32x2 weight = pk2(0.f);
+    uint32_t last_a = 0, last_b = 0;
 
     int c = 0;
     for (; c < n_chunks; c++) {
@@ -108,64 +117,112 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
         const int cnt = min(CHUNK, n - c * CHUNK);
         const Splat* sp = &buf[c & 1][0];
 
-        // classify: one record per thread against the eight 8x4 blocks of the tile
-        {
+        // classify: each thread tests two records against the four 8x8 regions of the tile
+#pragma unroll
+        for (int h = 0; h < CHUNK / BLEND_THREADS; h++) {
+            const int r = h * BLEND_THREADS + (int)threadIdx.x;
             unsigned m = 0;
-            if ((int)threadIdx.x < cnt) {
-                const float4 q0 = sp[threadIdx.x].q0;
-                m = subblock_mask(q0.x - tile_fx, q0.y - tile_fy, sp[threadIdx.x].q1, q0.z);
+            if (r < cnt) {
+                const float4 q0 = sp[r].q0;
+                m = region_mask(q0.x - tile_fx, q0.y - tile_fy, sp[r].q1, q0.z);
             }
-            s_mask[threadIdx.x] = (uint8_t)m;
+            s_mask[r] = (uint8_t)m;
         }
         __syncthreads();
 
-        if (!__all_sync(0xffffffffu, done)) {
+        if (!__all_sync(0xffffffffu, done_a && done_b)) {
             for (int k = 0; k * 32 < cnt; k++) {
                 unsigned word = __ballot_sync(0xffffffffu, (s_mask[k * 32 + lane] >> warp) & 1u);
                 while (word) {
                     const int j = k * 32 + __ffs(word) - 1;
                     word &= word - 1;
-                    if (done) continue;
                     const float4 q0 = sp[j].q0;
                     const float4 con_o = sp[j].q1;
-                    const float2 d = make_float2(q0.x - pixf.x, q0.y - pixf.y);
-                    const float power = pair_power(con_o, d.x, d.y);
-                    if (power > 0.0f) continue;
-                    if (power < q0.z) continue;  // certainly alpha < 1/255
-                    const float alpha = min(0.99f, con_o.w * expf(power));
-                    if (alpha < ALPHA_MIN) continue;
-                    const float test_T = T * (1 - alpha);
-                    if (test_T < T_MIN) {
-                        done = true;
-                        continue;
+                    const float dx = q0.x - pxf;
+                    const f32x2 dy2 = sub2(pk2(q0.y), pyf2);
+                    const f32x2 power2 = pair_power2(con_o, pk2(dx), dy2);
+                    float pa, pb;
+                    upk(power2, pa, pb);
+                    // a pixel takes part unless it is finished, power > 0, or alpha certainly < 1/255
+                    bool ma = !done_a && !(pa > 0.0f) && !(pa < q0.z);
+                    bool mb = !done_b && !(pb > 0.0f) && !(pb < q0.z);
+                    if (__any_sync(0xffffffffu, ma || mb)) {
+                        const f32x2 og2 = mul2(pk2(con_o.w), expf2(power2));
+                        float aa, ab;
+                        upk(og2, aa, ab);
+                        aa = min(0.99f, aa);
+                        ab = min(0.99f, ab);
+                        ma = ma && !(aa < ALPHA_MIN);
+                        mb = mb && !(ab < ALPHA_MIN);
+                        if (__any_sync(0xffffffffu, ma || mb)) {
+                            float Ta, Tb, tta, ttb;
+                            upk(T2, Ta, Tb);
+                            upk(mul2(T2, sub2(pk2(1.f), pk(aa, ab))), tta, ttb);  // test_T = T * (1 - alpha)
+                            if (ma && tta < T_MIN) {
+                                done_a = true;
+                                ma = false;
+                            }
+                            if (mb && ttb < T_MIN) {
+                                done_b = true;
+                                mb = false;
+                            }
+                            // a pixel that does not blend this record gets alpha = 0: every update below is then
+                            // the exact identity
+                            const f32x2 al2 = pk(ma ? aa : 0.f, mb ? ab : 0.f);
+                            const float4 q2 = sp[j].q2;
+                            float p0a, p0b, p1a, p1b, p2a, p2b, pda, pdb;
+                            upk(mul2(pk2(q2.x), al2), p0a, p0b);
+                            upk(mul2(pk2(q2.y), al2), p1a, p1b);
+                            upk(mul2(pk2(q2.z), al2), p2a, p2b);
+                            upk(mul2(pk2(q2.w), al2), pda, pdb);
+                            C0a = fmaf(p0a, Ta, C0a);
+                            C0b = fmaf(p0b, Tb, C0b);
+                            C1a = fmaf(p1a, Ta, C1a);
+                            C1b = fmaf(p1b, Tb, C1b);
+                            C2a = fmaf(p2a, Ta, C2a);
+                            C2b = fmaf(p2b, Tb, C2b);
+                            Da = fmaf(pda, Ta, Da);
+                            Db = fmaf(pdb, Tb, Db);
+                            fma2_acc(weight, al2, T2);
+                            T2 = pk(ma ? tta : Ta, mb ? ttb : Tb);
+                            const uint32_t pos1 = (uint32_t)(c * CHUNK + j + 1);
+                            last_a = ma ? pos1 : last_a;
+                            last_b = mb ? pos1 : last_b;
+                        }
                     }
-                    const float4 q2 = sp[j].q2;
-                    C0 += q2.x * alpha * T;
-                    C1 += q2.y * alpha * T;
-                    C2 += q2.z * alpha * T;
-                    weight += alpha * T;
-                    D += q2.w * alpha * T;
-                    T = test_T;
-                    last_contributor = (uint32_t)(c * CHUNK + j + 1);
                 }
-                if (__all_sync(0xffffffffu, done)) break;
+                if (__all_sync(0xffffffffu, done_a && done_b)) break;
             }
         }
         // everyone is finished with buf[c & 1] and s_mask; also the tile-wide early exit
-        if (__syncthreads_and(done)) break;
+        if (__syncthreads_and(done_a && done_b)) break;
     }
     // never leave with a bulk copy still in flight into our shared memory
     if (threadIdx.x == 0 && c < n_chunks && c + 1 < n_chunks) mbar_wait(&full[(c + 1) & 1], ((c + 1) >> 1) & 1);
 
-    if (inside) {
-        const size_t HW = (size_t)H * W;
-        const size_t pid = (size_t)py * W + px;
-        n_contrib[pid] = last_contributor;
-        out_color[pid] = C0 + T * __ldg(bg);
-        out_color[HW + pid] = C1 + T * __ldg(bg + 1);
-        out_color[2 * HW + pid] = C2 + T * __ldg(bg + 2);
-        out_alpha[pid] = weight;
-        out_depth[pid] = D;
+    const size_t HW = (size_t)H * W;
+    const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
+    float Ta, Tb, wa, wb;
+    upk(T2, Ta, Tb);
+    upk(weight, wa, wb);
+    const float c0a = C0a, c0b = C0b, c1a = C1a, c1b = C1b, c2a = C2a, c2b = C2b, da = Da, db = Db;
+    if (inside_a) {
+        const size_t pid = (size_t)pya * W + px;
+        n_contrib[pid] = last_a;
+        out_color[pid] = c0a + Ta * bg0;
+        out_color[HW + pid] = c1a + Ta * bg1;
+        out_color[2 * HW + pid] = c2a + Ta * bg2;
+        out_alpha[pid] = wa;
+        out_depth[pid] = da;
+    }
+    if (inside_b) {
+        const size_t pid = (size_t)pyb * W + px;
+        n_contrib[pid] = last_b;
+        out_color[pid] = c0b + Tb * bg0;
+        out_color[HW + pid] = c1b + Tb * bg1;
+        out_color[2 * HW + pid] = c2b + Tb * bg2;
+        out_alpha[pid] = wb;
+        out_depth[pid] = db;
     }
 }
 

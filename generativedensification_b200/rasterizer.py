@@ -78,6 +78,18 @@ def _f32c(t: torch.Tensor, device) -> torch.Tensor:
     return t.contiguous()
 
 
+def round_capacity(n: int) -> int:
+    """Round an instance capacity up to a coarse geometric grid (4 steps per octave).
+
+    Buffer sizes derived from it then repeat from frame to frame although the instance count drifts, so
+    torch's caching allocator hands the same blocks back instead of calling cudaMalloc / cudaFree (which
+    synchronise the device) whenever a scene changes a little."""
+    if n <= 4096:
+        return 4096
+    step = 1 << (n.bit_length() - 3)
+    return (n + step - 1) // step * step
+
+
 class _CapacityPredictor:
     """Remembers the last instance count per (device, P, H, W) to size the next frame's buffers."""
 
@@ -86,7 +98,7 @@ class _CapacityPredictor:
 
     def predict(self, key) -> int:
         r = self.last.get(key)
-        return 0 if r is None else int(r * 1.5) + 4096
+        return 0 if r is None else round_capacity(int(r * 1.5) + 4096)
 
     def update(self, key, r: int) -> None:
         self.last[key] = r
@@ -192,7 +204,7 @@ def _forward_impl(settings: GaussianRasterizationSettings, means3D, sh, colors_p
         _predictor.update(key, R)
         st.num_rendered = R
         if guess == 0 or R > guess:
-            render(R)
+            render(round_capacity(R))
         if settings.prefiltered:
             pass  # the reference traps on-device if a prefiltered point is culled; we do not abort the context
     return color, radii, depth, alpha, st

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .rasterizer import GaussianRasterizationSettings, _f32c, _predictor, _ptr, options
+from .rasterizer import GaussianRasterizationSettings, _f32c, _predictor, _ptr, options, round_capacity
 
 
 class CameraBatch:
@@ -152,7 +152,7 @@ def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scal
         _predictor.update(key, r_max)
         st.num_rendered = counts
         if guess == 0 or r_max > guess:
-            render(max(r_max, 1))
+            render(round_capacity(r_max))
     return color, radii, depth, alpha, st
 
 
