@@ -99,3 +99,58 @@ def gather_view_results(local: Dict[int, torch.Tensor], n_views: int, device) ->
         if int(seen.min()) != 1 or int(seen.max()) != 1:
             raise RuntimeError("view sharding did not cover every view exactly once")
     return vals
+
+
+class HostFeeder:
+    """Double-buffered host -> device feed of per-object Gaussian attribute dicts on a side stream.
+
+    The reference feeds its render loops from a DataLoader and uploads each batch with `.to(device)` on
+    the compute stream (lightning/network.py); here the upload of the next object overlaps the rendering
+    of the current one.  submit(host_dict) enqueues an upload (pinned host tensors) into the next free
+    slot; take() makes the compute stream wait for the oldest submitted slot and returns its device
+    tensors; release() marks that slot reusable once the work enqueued so far on the compute stream is done."""
+
+    def __init__(self, device, depth: int = 2):
+        self.device = device
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(device)
+        self.slots = [None] * depth
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [None] * depth
+        self.head = 0  # next slot to fill
+        self.tail = 0  # next slot to take
+        self.in_flight = 0
+        self.taken = None
+
+    def submit(self, host: Dict[str, torch.Tensor]) -> None:
+        if self.in_flight >= self.depth:
+            raise RuntimeError("HostFeeder: all slots are in flight; take()/release() first")
+        i = self.head
+        if self.slots[i] is None or any(self.slots[i][k].shape != v.shape for k, v in host.items()):
+            self.slots[i] = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
+        with torch.cuda.stream(self.copy_stream):
+            if self.free[i] is not None:
+                self.copy_stream.wait_event(self.free[i])  # the renders that read this slot have finished
+            for k, v in host.items():
+                self.slots[i][k].copy_(v, non_blocking=True)
+            self.ready[i].record(self.copy_stream)
+        self.head = (i + 1) % self.depth
+        self.in_flight += 1
+
+    def take(self) -> Dict[str, torch.Tensor]:
+        if self.in_flight == 0:
+            raise RuntimeError("HostFeeder: nothing submitted")
+        i = self.tail
+        torch.cuda.current_stream(self.device).wait_event(self.ready[i])
+        self.taken = i
+        self.tail = (i + 1) % self.depth
+        return {k: v.detach() for k, v in self.slots[i].items()}
+
+    def release(self) -> None:
+        if self.taken is None:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.free[self.taken] = ev
+        self.taken = None
+        self.in_flight -= 1

@@ -1,0 +1,27 @@
+"""profiles/traffic.json from an `ncu --set full` report: DRAM bytes (read + write) per launch of each of our kernels.
+
+    python tools/make_traffic.py gpurun_out/prof_r1_all.ncu-rep > profiles/traffic.json
+bench.py reads it for `roofline.traffic` (the value belongs to the workload of tools/prof_step.py = the bench workload)."""
+import csv
+import json
+import subprocess
+import sys
+
+STAGE = {"project_kernel": "project", "tile_scan_kernel": "tile_scan", "emit_kernel": "emit", "tile_sort_kernel": "tile_sort",
+         "blend_forward_kernel": "blend_fwd", "blend_backward_kernel": "blend_bwd", "gauss_backward_kernel": "gauss_bwd"}
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, units = rows[0], rows[1]
+res = {}
+for r in rows[2:]:
+    d = dict(zip(hdr, r))
+    stage = next((v for k, v in STAGE.items() if k in d["Kernel Name"]), None)
+    if stage is None or stage in res:
+        continue
+    rd = float(d["dram__bytes_read.sum"]) * UNIT[units[hdr.index("dram__bytes_read.sum")]]
+    wr = float(d["dram__bytes_write.sum"]) * UNIT[units[hdr.index("dram__bytes_write.sum")]]
+    res[stage] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
+                  "gpu_time_us_under_ncu": float(d["gpu__time_duration.sum"]), "source": sys.argv[1].split("/")[-1]}
+json.dump(res, sys.stdout, indent=1)
