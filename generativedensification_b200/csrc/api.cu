@@ -167,6 +167,7 @@ int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, in
         a.scales = g.scales; a.scale_modifier = g.scale_modifier; a.rotations = g.rotations;
         a.cov3D_precomp = g.cov3D_precomp;
         a.prefiltered = prefiltered;
+        a.raw_params = (flags & GDR_FLAG_RAW_PARAMS) ? 1 : 0;
         a.cull = (flags & GDR_FLAG_NO_TILE_CULL) ? 0 : 1;
         a.vw = vw;
         a.radii = radii;

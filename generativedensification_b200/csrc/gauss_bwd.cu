@@ -31,6 +31,7 @@ __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
 constexpr int GB_THREADS = 128;
+constexpr int GRAD_RAW_PARAMS = 32;  // == GDR_GRAD_RAW_PARAMS (include/gdr.h)
 
 template <bool ACC>
 __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, const int idx);
@@ -77,7 +78,15 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
     const int M = a.M;
 
     if (a.dL_dmeans2D) put4<ACC>(a.dL_dmeans2D + (size_t)idx * 4, g_mean2D);
-    if (a.dL_dopacity) put<ACC>(a.dL_dopacity + idx, g_conic_op.w);
+    const bool raw = (a.grad_mask & GRAD_RAW_PARAMS) != 0;  // gradients w.r.t. logits / log-scales / raw quaternions
+    if (a.dL_dopacity) {
+        float g = g_conic_op.w;
+        if (raw) {  // d sigmoid: o (1 - o); the activated opacity is in the saved record (0 for culled Gaussians)
+            const float o = geom.splat[idx].q1.w;
+            g = g * (1.f - o) * o;
+        }
+        put<ACC>(a.dL_dopacity + idx, g);
+    }
     if (a.dL_dcolors) {
         put<ACC>(a.dL_dcolors + (size_t)idx * 3 + 0, g_rgb_depth.x);
         put<ACC>(a.dL_dcolors + (size_t)idx * 3 + 1, g_rgb_depth.y);
@@ -292,15 +301,20 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
 
     // ---- cov3D -> scale, rotation : backward.cu:278-341 ----
     if (a.scales != nullptr && (a.dL_dscales || a.dL_drotations)) {
-        const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+        float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+        float3 sc = make_float3(a.scales[(size_t)idx * 3], a.scales[(size_t)idx * 3 + 1], a.scales[(size_t)idx * 3 + 2]);
+        float qn = 1.f;
+        if (raw) {
+            qn = fmaxf(quat_norm(q), 1e-12f);
+            q = act_rotation(q);
+            sc = make_float3(act_scale(sc.x), act_scale(sc.y), act_scale(sc.z));
+        }
         const float r = q.x, x = q.y, y = q.z, z = q.w;
         Mat3 R;
         R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
         R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
         R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
-        const float3 s = make_float3(a.scale_modifier * a.scales[(size_t)idx * 3],
-                                     a.scale_modifier * a.scales[(size_t)idx * 3 + 1],
-                                     a.scale_modifier * a.scales[(size_t)idx * 3 + 2]);
+        const float3 s = make_float3(a.scale_modifier * sc.x, a.scale_modifier * sc.y, a.scale_modifier * sc.z);
         Mat3 S;
 #pragma unroll
         for (int c = 0; c < 3; c++)
@@ -321,9 +335,11 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
         const Mat3 Rt = mat3_transpose(R);
         Mat3 dL_dMt = mat3_transpose(dL_dM);
         if (a.dL_dscales) {
-            put<ACC>(a.dL_dscales + (size_t)idx * 3 + 0, Rt.m[0][0] * dL_dMt.m[0][0] + Rt.m[0][1] * dL_dMt.m[0][1] + Rt.m[0][2] * dL_dMt.m[0][2]);
-            put<ACC>(a.dL_dscales + (size_t)idx * 3 + 1, Rt.m[1][0] * dL_dMt.m[1][0] + Rt.m[1][1] * dL_dMt.m[1][1] + Rt.m[1][2] * dL_dMt.m[1][2]);
-            put<ACC>(a.dL_dscales + (size_t)idx * 3 + 2, Rt.m[2][0] * dL_dMt.m[2][0] + Rt.m[2][1] * dL_dMt.m[2][1] + Rt.m[2][2] * dL_dMt.m[2][2]);
+            // d exp: multiply by the activated scale when the inputs are log-scales
+            const float k0 = raw ? sc.x : 1.f, k1 = raw ? sc.y : 1.f, k2 = raw ? sc.z : 1.f;
+            put<ACC>(a.dL_dscales + (size_t)idx * 3 + 0, k0 * (Rt.m[0][0] * dL_dMt.m[0][0] + Rt.m[0][1] * dL_dMt.m[0][1] + Rt.m[0][2] * dL_dMt.m[0][2]));
+            put<ACC>(a.dL_dscales + (size_t)idx * 3 + 1, k1 * (Rt.m[1][0] * dL_dMt.m[1][0] + Rt.m[1][1] * dL_dMt.m[1][1] + Rt.m[1][2] * dL_dMt.m[1][2]));
+            put<ACC>(a.dL_dscales + (size_t)idx * 3 + 2, k2 * (Rt.m[2][0] * dL_dMt.m[2][0] + Rt.m[2][1] * dL_dMt.m[2][1] + Rt.m[2][2] * dL_dMt.m[2][2]));
         }
 #pragma unroll
         for (int rr = 0; rr < 3; rr++) {
@@ -337,6 +353,12 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
             dq.y = 2 * y * (dL_dMt.m[1][0] + dL_dMt.m[0][1]) + 2 * z * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) + 2 * r * (dL_dMt.m[1][2] - dL_dMt.m[2][1]) - 4 * x * (dL_dMt.m[2][2] + dL_dMt.m[1][1]);
             dq.z = 2 * x * (dL_dMt.m[1][0] + dL_dMt.m[0][1]) + 2 * r * (dL_dMt.m[2][0] - dL_dMt.m[0][2]) + 2 * z * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * y * (dL_dMt.m[2][2] + dL_dMt.m[0][0]);
             dq.w = 2 * r * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * x * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) + 2 * y * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * z * (dL_dMt.m[1][1] + dL_dMt.m[0][0]);
+            if (raw) {  // through q / ||q||: (g - q^ (q^ . g)) / ||q||
+                const float d = q.x * dq.x + q.y * dq.y + q.z * dq.z + q.w * dq.w;
+                const float inv = 1.f / qn;
+                dq = make_float4((dq.x - q.x * d) * inv, (dq.y - q.y * d) * inv, (dq.z - q.z * d) * inv,
+                                 (dq.w - q.w * d) * inv);
+            }
             put4<ACC>(a.dL_drotations + (size_t)idx * 4, dq);
         }
     } else if (!ACC) {

@@ -22,6 +22,7 @@ struct ProjectArgs {
     const float* rotations;
     const float* cov3D_precomp;
     int prefiltered;
+    int raw_params;  // opacities are logits, scales are log-scales, rotations are un-normalised (GDR_FLAG_RAW_PARAMS)
     int cull;  // exact tile-level culling of (Gaussian, tile) pairs that cannot reach alpha = 1/255
     Views vw;          // cameras + per-view strides; every per-view pointer below is view 0's
     int32_t* radii;    // [V][P]

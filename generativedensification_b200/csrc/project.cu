@@ -203,9 +203,13 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
 #pragma unroll
                 for (int k = 0; k < 6; k++) cov3D[k] = __ldg(a.cov3D_precomp + (size_t)idx * 6 + k);
             } else {
-                const float3 sc = make_float3(s_scale[3 * threadIdx.x], s_scale[3 * threadIdx.x + 1],
-                                              s_scale[3 * threadIdx.x + 2]);
-                const float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+                float3 sc = make_float3(s_scale[3 * threadIdx.x], s_scale[3 * threadIdx.x + 1],
+                                        s_scale[3 * threadIdx.x + 2]);
+                float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+                if (a.raw_params) {  // activation-fused inputs (renderer.py:225-230 done here)
+                    sc = make_float3(act_scale(sc.x), act_scale(sc.y), act_scale(sc.z));
+                    q = act_rotation(q);
+                }
                 cov3d_from_scale_rot(sc, a.scale_modifier, q, cov3D);
             }
             const float3 cov = cov2d_ewa(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov3D, viewmatrix);
@@ -231,7 +235,8 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
                                           __ldg(a.colors_precomp + (size_t)idx * 3 + 1),
                                           __ldg(a.colors_precomp + (size_t)idx * 3 + 2));
                     }
-                    const float opacity = __ldg(a.opacities + idx);
+                    float opacity = __ldg(a.opacities + idx);
+                    if (a.raw_params) opacity = act_opacity(opacity);
                     // Conservative reject threshold: power < thr  =>  opacity*exp(power) < 1/255 for certain
                     // (1e-4 of slack in the exponent dwarfs every rounding error of the exact test).
                     // (opacity <= 0 can never reach 1/255: reject everything; NaN opacity: never reject.)

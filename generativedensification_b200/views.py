@@ -89,7 +89,8 @@ class _ViewsState:
     __slots__ = ("geom", "img", "stream_buf", "capacity", "num_rendered", "P", "M", "V")
 
 
-def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp):
+def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                   raw_params: bool = False):
     lib = _lib.load()
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -119,6 +120,8 @@ def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scal
         st.img = torch.empty(V * _lib.query_bytes("gdr_image_state_bytes", W, H), dtype=torch.uint8, device=device)
         mailbox = _mailbox_views(device, V)
         flags = 0 if options["tile_cull"] else _lib.FLAG_NO_TILE_CULL
+        if raw_params:
+            flags |= _lib.FLAG_RAW_PARAMS
         _lib.check(lib.gdr_views_forward_project(
             V, P, cb.sh_degree, st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
             _ptr(scales), cb.scale_modifier, _ptr(rotations), _ptr(cov3Ds_precomp), cb.cams.data_ptr(),
@@ -156,7 +159,8 @@ def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scal
     return color, radii, depth, alpha, st
 
 
-def _backward_views(cb: CameraBatch, st: _ViewsState, saved, grad_color, grad_depth, grad_alpha, needs):
+def _backward_views(cb: CameraBatch, st: _ViewsState, saved, grad_color, grad_depth, grad_alpha, needs,
+                    raw_params: bool = False):
     lib = _lib.load()
     colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, alpha = saved
     device = means3D.device
@@ -195,6 +199,8 @@ def _backward_views(cb: CameraBatch, st: _ViewsState, saved, grad_color, grad_de
         out["cov3D"] = torch.empty(P, 6, **f32)
     if mask == 0:
         return out
+    if raw_params:
+        mask |= _lib.GRAD_RAW_PARAMS
     with torch.cuda.device(device):
         grad_color = _f32c(grad_color, device)
         grad_depth = None if grad_depth is None else _f32c(grad_depth, device)
@@ -213,10 +219,12 @@ def _backward_views(cb: CameraBatch, st: _ViewsState, saved, grad_color, grad_de
 
 class _RasterizeViews(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, cameras):
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, cameras,
+                raw_params=False):
         color, radii, depth, alpha, st = _forward_views(cameras, means3D, sh, colors_precomp, opacities, scales,
-                                                        rotations, cov3Ds_precomp)
+                                                        rotations, cov3Ds_precomp, raw_params)
         ctx.cameras = cameras
+        ctx.raw_params = bool(raw_params)
         ctx.state = st
         ctx.num_rendered = st.num_rendered
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, alpha)
@@ -231,16 +239,21 @@ class _RasterizeViews(torch.autograd.Function):
         means3D = saved[1]
         if grad_color is None:
             grad_color = torch.zeros(cb.V, 3, cb.height, cb.width, dtype=torch.float32, device=means3D.device)
-        g = _backward_views(cb, st, saved, grad_color, grad_depth, grad_alpha, tuple(ctx.needs_input_grad[:8]))
+        g = _backward_views(cb, st, saved, grad_color, grad_depth, grad_alpha, tuple(ctx.needs_input_grad[:8]),
+                            ctx.raw_params)
         return (g["means3D"], g["means2D"], g["sh"], g["colors"], g["opacity"], g["scales"], g["rot"], g["cov3D"],
-                None)
+                None, None)
 
 
 def rasterize_views(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                    cameras: CameraBatch):
-    """Batched counterpart of rasterize_gaussians(); `cameras` replaces `raster_settings`."""
+                    cameras: CameraBatch, raw_params: bool = False):
+    """Batched counterpart of rasterize_gaussians(); `cameras` replaces `raster_settings`.
+
+    raw_params=True: `opacities` are logits, `scales` log-scales and `rotations` un-normalised
+    quaternions; sigmoid / exp / normalise run inside the projection kernel (bit-identical to activating
+    with torch first) and the returned gradients are w.r.t. the raw parameters."""
     return _RasterizeViews.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                                 cameras)
+                                 cameras, raw_params)
 
 
 class MultiViewRasterizer(nn.Module):
@@ -255,7 +268,7 @@ class MultiViewRasterizer(nn.Module):
             CameraBatch.from_settings(list(raster_settings))
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None):
+                cov3D_precomp=None, raw_params: bool = False):
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
             raise Exception('Please provide excatly one of either SHs or precomputed colors!')
         if ((scales is None or rotations is None) and cov3D_precomp is None) or \
@@ -264,20 +277,28 @@ class MultiViewRasterizer(nn.Module):
         e = torch.Tensor([])
         return rasterize_views(means3D, means2D, e if shs is None else shs, e if colors_precomp is None else colors_precomp,
                                opacities, e if scales is None else scales, e if rotations is None else rotations,
-                               e if cov3D_precomp is None else cov3D_precomp, self.cameras)
+                               e if cov3D_precomp is None else cov3D_precomp, self.cameras, raw_params)
 
 
 def render_images(cameras, centers, shs, opacity, scales, rotations, screenspace_points: Optional[torch.Tensor] = None,
                   opacity_activation=torch.sigmoid, scaling_activation=torch.exp,
-                  rotation_activation=torch.nn.functional.normalize, prex: str = "") -> dict:
+                  rotation_activation=torch.nn.functional.normalize, prex: str = "",
+                  fused_activations: bool = False) -> dict:
     """Renderer.render_img (lightning/renderer.py:209-272) for V views at once: activations, rasterize,
-    clamp and the HWC permutes, stacked over the views: image [V,H,W,3], depth [V,H,W,1], acc_map [V,H,W]."""
+    clamp and the HWC permutes, stacked over the views: image [V,H,W,3], depth [V,H,W,1], acc_map [V,H,W].
+
+    fused_activations=True applies the reference's default activations (sigmoid / exp / normalize) inside
+    the projection kernel instead of three torch passes (and their autograd nodes); same bits out."""
     rast = cameras if isinstance(cameras, MultiViewRasterizer) else MultiViewRasterizer(cameras)
     if screenspace_points is None:
         screenspace_points = torch.zeros(centers.shape[0], 4, dtype=centers.dtype, device=centers.device,
                                          requires_grad=True) + 0
-    image, radii, depth, alpha = rast(means3D=centers, means2D=screenspace_points, shs=shs,
-                                      opacities=opacity_activation(opacity), scales=scaling_activation(scales),
-                                      rotations=rotation_activation(rotations))
+    if fused_activations:
+        image, radii, depth, alpha = rast(means3D=centers, means2D=screenspace_points, shs=shs, opacities=opacity,
+                                          scales=scales, rotations=rotations, raw_params=True)
+    else:
+        image, radii, depth, alpha = rast(means3D=centers, means2D=screenspace_points, shs=shs,
+                                          opacities=opacity_activation(opacity), scales=scaling_activation(scales),
+                                          rotations=rotation_activation(rotations))
     return {f"image{prex}": image.clamp(0, 1).permute(0, 2, 3, 1), f"depth{prex}": depth.permute(0, 2, 3, 1),
             f"acc_map{prex}": alpha.squeeze(1)}

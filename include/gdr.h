@@ -73,11 +73,18 @@ extern "C" {
 #define GDR_GRAD_OPACITY 8
 #define GDR_GRAD_COV 16    /* dL/dscales + dL/drotations, or dL/dcov3D_precomp */
 #define GDR_GRAD_ALL 31
+#define GDR_GRAD_RAW_PARAMS 32 /* the forward ran with GDR_FLAG_RAW_PARAMS: return dL/dopacity, dL/dscales, dL/drotations
+                                  w.r.t. the RAW parameters (through sigmoid / exp / normalise); `scales` and `rotations`
+                                  passed to the backward are the raw ones */
 
 /* flags for gdr_forward_project / gdr_forward_render (must be identical in both calls of a frame) */
 #define GDR_FLAG_NO_TILE_CULL 1 /* bin every tile of the reference's 3-sigma rectangle, exactly like the reference.
                                    Default (0): drop (Gaussian, tile) pairs that provably cannot reach
                                    alpha = 1/255 in the tile -- outputs are unchanged, R shrinks. */
+#define GDR_FLAG_RAW_PARAMS 2   /* activation-fused inputs: `opacities` are logits, `scales` log-scales,
+                                   `rotations` un-normalised quaternions; sigmoid / exp / normalise (what
+                                   Renderer.render_img applies first, lightning/renderer.py:95-101, 225-230) run inside
+                                   the projection kernel with torch's exact roundings.  gdr_forward_project only. */
 
 GDR_API int gdr_abi_version(void);
 GDR_API const char* gdr_last_error(void);

@@ -134,3 +134,30 @@ def test_render_images_matches_reference_renderer_glue(device):
         assert torch.equal(out["image"][v], img.clamp(0, 1).permute(1, 2, 0))
         assert torch.equal(out["depth"][v], dep.permute(1, 2, 0))
         assert torch.equal(out["acc_map"][v], acc.squeeze(0))
+
+
+def test_fused_activations_match_torch_activations(device):
+    """sigmoid / exp / normalise inside the projection kernel == torch activations first
+    (forward bit-identical; gradients w.r.t. the RAW parameters within tolerance)."""
+    from generativedensification_b200.views import render_images
+
+    V, W, H, P = 3, 128, 96, 6000
+    st = _settings(V, W, H, device)
+    gen = torch.Generator().manual_seed(31)
+    raw = dict(centers=(torch.rand(P, 3, generator=gen) - 0.5), shs=torch.randn(P, 4, 3, generator=gen),
+               opacity=torch.randn(P, 1, generator=gen) * 1.5 - 1.0, scales=torch.randn(P, 3, generator=gen) * 0.3 - 4.0,
+               rotations=torch.randn(P, 4, generator=gen) * 2.0)
+    outs = {}
+    for fused in (False, True):
+        leaves = {k: v.to(device).clone().requires_grad_(True) for k, v in raw.items()}
+        o = render_images(st, leaves["centers"], leaves["shs"], leaves["opacity"], leaves["scales"],
+                          leaves["rotations"], fused_activations=fused)
+        g = torch.Generator().manual_seed(32)
+        loss = sum((o[k] * torch.randn(o[k].shape, generator=g).to(device)).sum() for k in ("image", "depth", "acc_map"))
+        grads = torch.autograd.grad(loss, list(leaves.values()))
+        outs[fused] = (o, dict(zip(leaves, grads)))
+    for k in ("image", "depth", "acc_map"):
+        assert torch.equal(outs[True][0][k], outs[False][0][k]), k
+    for k in raw:
+        err, _ = U.grad_errors(outs[True][1][k].cpu().numpy(), outs[False][1][k].cpu().numpy())
+        assert err <= 1e-4, (k, err)
