@@ -149,7 +149,7 @@ int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, in
     }
     gdr::ImageState img = gdr::ImageState::carve(image_state, W, H);
     const int T = tiles_of(W, H);
-    const size_t hdr_bytes = sizeof(uint32_t) * gdr::IMG_HEADER_WORDS, cnt_bytes = sizeof(uint32_t) * (size_t)T;
+    const size_t hdr_bytes = sizeof(uint32_t) * gdr::IMG_HEADER_WORDS, cnt_bytes = sizeof(uint32_t) * (size_t)T * gdr::SUBBINS;
     if (vw.V == 1) {
         GDR_CUDA(cudaMemsetAsync(img.header, 0, hdr_bytes, s), "memset(header)");
         GDR_CUDA(cudaMemsetAsync(img.tile_counter, 0, cnt_bytes, s), "memset(tile_counter)");

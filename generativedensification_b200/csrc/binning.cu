@@ -10,11 +10,14 @@
 // B200-first structure:
 //   tile_scan   one CTA scans the per-tile bin counters filled by the project
 //               kernel -> tile_offsets (the reference's `ranges`), R.
-//   emit        warp-cooperative walk over (Gaussian, tile) pairs; one
-//               aggregated atomic per distinct tile claims slots in the tile's
-//               segment; writes the key (depth bits << 32 | idx).  Slot order
-//               within a segment is arbitrary -- the keys are unique, so the
-//               sort below makes the result deterministic.
+//   emit        one thread per Gaussian replays the kept-tile bitmask the projection
+//               kernel recorded (rectangles of <= 64 tiles: no culling test, no
+//               cooperation, the slot claims of one thread overlap in flight);
+//               larger rectangles take a warp-cooperative walk over (Gaussian,
+//               tile) pairs with one aggregated atomic per distinct tile.  Writes
+//               the key (depth bits << 32 | idx).  Slot order within a segment is
+//               arbitrary -- the keys are unique, so the sort below makes the
+//               result deterministic.
 //   tile_sort   one CTA per tile sorts its segment in shared memory (bitonic on
 //               u64; segments longer than the smem chunk are chunk-sorted and
 //               merged through global memory) and writes the tile's depth-sorted
@@ -31,123 +34,210 @@ namespace {
 
 constexpr int SCAN_THREADS = 1024;
 
+static_assert(SUBBINS % 4 == 0, "tile_scan_kernel moves a tile's sub-bin counters as 128-bit words");
+constexpr int SUBQ = SUBBINS / 4;  // 128-bit words per tile
+
+// One CTA per view; thread t of chunk c owns tile c * SCAN_THREADS + t and reads / writes its SUBBINS
+// counters as aligned 128-bit words (coalesced across the CTA).  Pass 1 buckets the tiles by
+// floor(log2(count)) for the heaviest-first tile order; pass 2 is a chunked block scan with a running carry.
 __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageState img0, size_t img_stride) {
-    const ImageState img = img0.at(blockIdx.x, img_stride);  // one CTA per view
+    const ImageState img = img0.at(blockIdx.x, img_stride);
     __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t warp_max[32];
     __shared__ uint32_t bucket_count[33];  // tiles per floor(log2(count)) + 1 bucket; bucket 0 = empty tiles
     __shared__ uint32_t bucket_base[33];
-    const int tid = threadIdx.x;
+    __shared__ uint32_t s_carry, s_max;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid < 33) bucket_count[tid] = 0;
+    if (tid == 0) {
+        s_carry = 0;
+        s_max = 0;
+    }
     __syncthreads();
-    const int per = (T + SCAN_THREADS - 1) / SCAN_THREADS;
-    const int b = min(T, tid * per), e = min(T, b + per);
-    uint32_t local = 0, lmax = 0;
-    for (int i = b; i < e; i++) {
-        const uint32_t c = img.tile_counter[i];
-        local += c;
+    uint4* counters = reinterpret_cast<uint4*>(img.tile_counter);
+    uint32_t lmax = 0;
+    for (int i = tid; i < T; i += SCAN_THREADS) {
+        uint32_t c = 0;
+#pragma unroll
+        for (int q = 0; q < SUBQ; q++) {
+            const uint4 a = counters[SUBQ * i + q];
+            c += a.x + a.y + a.z + a.w;
+        }
         lmax = max(lmax, c);
         atomicAdd(&bucket_count[c ? 32 - __clz(c) : 0], 1u);
     }
-    // block exclusive scan of `local`
-    const int lane = tid & 31, wid = tid >> 5;
-    int incl = warp_incl_scan((int)local);
-    uint32_t m = lmax;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-    if (lane == 31) warp_sums[wid] = (uint32_t)incl;
-    if (lane == 0) warp_max[wid] = m;
+    lmax = __reduce_max_sync(0xffffffffu, lmax);
+    if (lane == 0) atomicMax(&s_max, lmax);
     __syncthreads();
-    if (wid == 0) {
-        const uint32_t v = warp_sums[lane];
-        const int s = warp_incl_scan((int)v);
-        warp_sums[lane] = (uint32_t)s - v;  // exclusive
-        uint32_t mm = warp_max[lane];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mm = max(mm, __shfl_xor_sync(0xffffffffu, mm, d));
-        if (lane == 31) {
-            img.header[HDR_NUM_RENDERED] = (uint32_t)s;
-            img.tile_offsets[T] = (uint32_t)s;
-        }
-        if (lane == 0) img.header[HDR_MAX_TILE] = mm;
-    }
     if (tid == 0) {  // heaviest bucket first: longest-processing-time-first order for the blend kernels
         uint32_t acc = 0;
         for (int k = 32; k >= 0; k--) {
             bucket_base[k] = acc;
             acc += bucket_count[k];
         }
+        img.header[HDR_MAX_TILE] = s_max;
     }
     __syncthreads();
-    uint32_t run = warp_sums[wid] + (uint32_t)incl - local;
-    for (int i = b; i < e; i++) {
-        const uint32_t c = img.tile_counter[i];
-        img.tile_offsets[i] = run;
-        img.tile_counter[i] = 0;  // becomes the emit cursor
-        run += c;
-        img.tile_order[atomicAdd(&bucket_base[c ? 32 - __clz(c) : 0], 1u)] = (uint32_t)i;
+    for (int base = 0; base < T; base += SCAN_THREADS) {
+        const int i = base + tid;
+        uint4 a[SUBQ];
+        uint32_t c = 0;
+#pragma unroll
+        for (int q = 0; q < SUBQ; q++) {
+            a[q] = i < T ? counters[SUBQ * i + q] : make_uint4(0, 0, 0, 0);
+            c += a[q].x + a[q].y + a[q].z + a[q].w;
+        }
+        const int incl = warp_incl_scan((int)c);
+        if (lane == 31) warp_sums[wid] = (uint32_t)incl;
+        __syncthreads();
+        if (wid == 0) {  // exclusive scan of the 32 warp totals
+            const uint32_t ws = warp_sums[lane];
+            warp_sums[lane] = (uint32_t)warp_incl_scan((int)ws) - ws;
+        }
+        __syncthreads();
+        uint32_t run = s_carry + warp_sums[wid] + (uint32_t)incl - c;
+        if (i < T) {
+            img.tile_offsets[i] = run;
+            uint4* so = reinterpret_cast<uint4*>(img.sub_offsets);
+            uint32_t r = run;
+#pragma unroll
+            for (int q = 0; q < SUBQ; q++) {
+                uint4 o;
+                o.x = r;
+                o.y = o.x + a[q].x;
+                o.z = o.y + a[q].y;
+                o.w = o.z + a[q].z;
+                r = o.w + a[q].w;
+                so[SUBQ * i + q] = o;
+                counters[SUBQ * i + q] = make_uint4(0, 0, 0, 0);  // the counters become the emit cursors
+            }
+            img.tile_order[atomicAdd(&bucket_base[c ? 32 - __clz(c) : 0], 1u)] = (uint32_t)i;
+        }
+        __syncthreads();
+        if (tid == SCAN_THREADS - 1) s_carry = run + c;  // total up to and including this chunk
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const uint32_t total = s_carry;
+        img.header[HDR_NUM_RENDERED] = total;
+        img.tile_offsets[T] = total;
+        img.sub_offsets[T * SUBBINS] = total;
     }
 }
 
 constexpr int EMIT_THREADS = 128;
+
+// One instance: claim a slot of the tile's segment and write the key (depth bits << 32 | Gaussian index).
+__device__ __forceinline__ bool emit_one(int bin, uint64_t key, const uint32_t* __restrict__ sub_offsets,
+                                         uint32_t* __restrict__ cursor, uint64_t* __restrict__ keys, int64_t capacity,
+                                         uint32_t claim_base) {
+    const uint64_t pos = (uint64_t)__ldg(&sub_offsets[bin]) + claim_base;
+    if ((int64_t)pos < capacity && pos < (uint64_t)__ldg(&sub_offsets[bin + 1])) {
+        keys[pos] = key;
+        return true;
+    }
+    return false;
+}
 
 __global__ void __launch_bounds__(EMIT_THREADS)
 emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii0, GeomState geom0, ImageState img0,
             uint64_t* __restrict__ keys0, int64_t capacity, int cull, size_t geom_stride, size_t img_stride) {
     const int v = blockIdx.y;
     const int32_t* __restrict__ radii = radii0 + (size_t)v * P;
-    const Splat* __restrict__ splat = geom0.at(v, geom_stride).splat;
+    const GeomState geom = geom0.at(v, geom_stride);
+    const Splat* __restrict__ splat = geom.splat;
     const ImageState img = img0.at(v, img_stride);
-    const uint32_t* __restrict__ tile_offsets = img.tile_offsets;
+    const uint32_t* __restrict__ sub_offsets = img.sub_offsets;
     uint32_t* __restrict__ cursor = img.tile_counter;
     uint32_t* __restrict__ header = img.header;
     uint64_t* __restrict__ keys = keys0 + (size_t)v * capacity;
     const int n_vblocks = (P + EMIT_THREADS - 1) / EMIT_THREADS;
     bool overflow = false;
     for (int vb = blockIdx.x; vb < n_vblocks; vb += gridDim.x) {  // virtual blocks: balanced single wave
-    const int idx = vb * EMIT_THREADS + threadIdx.x;
-    int n = 0, x0 = 0, y0 = 0, w = 0;
-    uint32_t depth_bits = 0;
-    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
-    if (idx < P) {
-        const int r = radii[idx];
-        if (r > 0) {
+        const int idx = vb * EMIT_THREADS + threadIdx.x;
+        int n = 0, x0 = 0, y0 = 0, w = 0;
+        uint32_t depth_bits = 0;
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+        unsigned long long m = 0ull;
+        if (idx < P) {
+            // four independent loads (one round trip), then the rectangle
+            const int r = radii[idx];
             q0 = __ldg(&splat[idx].q0);
-            q1 = __ldg(&splat[idx].q1);
-            int x1, y1;
-            tile_rect(q0.x, q0.y, r, gx, gy, x0, y0, x1, y1);
-            w = x1 - x0;
-            n = w * (y1 - y0);
             depth_bits = __float_as_uint(__ldg(&splat[idx].q2.w));
+            m = geom.tile_mask[idx];
+            if (r > 0) {
+                int x1, y1;
+                tile_rect(q0.x, q0.y, r, gx, gy, x0, y0, x1, y1);
+                w = x1 - x0;
+                n = w * (y1 - y0);
+            }
         }
-    }
-    const int lane = (int)lane_id();
-    warp_foreach_tile(n, x0, y0, w, gx, [&](int tile, int owner, int, bool valid, unsigned) {
-        const uint32_t o_depth = __shfl_sync(0xffffffffu, depth_bits, owner);
-        const int o_idx = __shfl_sync(0xffffffffu, idx, owner);
-        bool keep = valid;
-        if (cull) {  // the identical test project_kernel used when it counted this tile
-            const float cx = __shfl_sync(0xffffffffu, q0.x, owner), cy = __shfl_sync(0xffffffffu, q0.y, owner);
-            const float thr = __shfl_sync(0xffffffffu, q0.z, owner);
-            const float A = __shfl_sync(0xffffffffu, q1.x, owner), B = __shfl_sync(0xffffffffu, q1.y, owner);
-            const float C = __shfl_sync(0xffffffffu, q1.z, owner);
-            const float tx0 = (float)((tile % gx) * TILE), ty0 = (float)((tile / gx) * TILE);
-            keep = valid && !splat_misses_rect(cx, cy, A, B, C, thr, tx0, ty0, tx0 + (TILE - 1), ty0 + (TILE - 1));
+        const uint64_t key = ((uint64_t)depth_bits << 32) | (uint32_t)idx;
+        if (n > 0 && n <= 64) {
+            // The common case: replay the kept-tile bitmask the projection kernel recorded for this Gaussian,
+            // one slot claim per kept tile.  Four claims per round with their segment bounds: the atomics and
+            // the loads are all issued before the first result is needed, so their round trips overlap.
+            const uint32_t inv_w = (65536u + (uint32_t)w - 1u) / (uint32_t)w;  // local / w for local < 64, w <= 64
+            while (m) {
+                int bins[4];  // sub-bin ids: tile * SUBBINS + idx % SUBBINS
+                uint32_t base[4], lo[4], hi[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    bins[u] = -1;
+                    if (m) {
+                        const int local = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const int row = (int)(((uint32_t)local * inv_w) >> 16);
+                        bins[u] = ((y0 + row) * gx + x0 + (local - row * w)) * SUBBINS + (idx & (SUBBINS - 1));
+                        lo[u] = __ldg(&sub_offsets[bins[u]]);
+                        hi[u] = __ldg(&sub_offsets[bins[u] + 1]);
+                        base[u] = atomicAdd(&cursor[bins[u]], 1u);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (bins[u] >= 0) {
+                        const uint64_t pos = (uint64_t)lo[u] + base[u];
+                        if ((int64_t)pos < capacity && pos < (uint64_t)hi[u])
+                            keys[pos] = key;
+                        else
+                            overflow = true;
+                    }
+                }
+            }
+            n = 0;  // done; takes no part in the cooperative walk below
+        } else if (n > 64) {
+            q1 = __ldg(&splat[idx].q1);
         }
-        const unsigned active = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const unsigned peers = __match_any_sync(active, tile);
-            const int leader = __ffs(peers) - 1;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(&cursor[tile], (unsigned)__popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            const uint64_t pos = (uint64_t)__ldg(&tile_offsets[tile]) + base + __popc(peers & lanemask_lt());
-            if ((int64_t)pos < capacity && pos < (uint64_t)__ldg(&tile_offsets[tile + 1]))
-                keys[pos] = ((uint64_t)o_depth << 32) | (uint32_t)o_idx;
-            else
-                overflow = true;
+        // Rectangles of more than 64 tiles (large splats): warp-cooperative walk over the (Gaussian, tile) pairs
+        // with the culling test repeated exactly as the projection kernel counted it.
+        if (__any_sync(0xffffffffu, n > 0)) {
+            const int lane = (int)lane_id();
+            warp_foreach_tile(n, x0, y0, w, gx, [&](int tile, int owner, int, bool valid, unsigned) {
+                const uint32_t o_depth = __shfl_sync(0xffffffffu, depth_bits, owner);
+                const int o_idx = __shfl_sync(0xffffffffu, idx, owner);
+                bool keep = valid;
+                if (cull) {  // the identical test project_kernel used when it counted this tile
+                    const float cx = __shfl_sync(0xffffffffu, q0.x, owner), cy = __shfl_sync(0xffffffffu, q0.y, owner);
+                    const float thr = __shfl_sync(0xffffffffu, q0.z, owner);
+                    const float A = __shfl_sync(0xffffffffu, q1.x, owner), B = __shfl_sync(0xffffffffu, q1.y, owner);
+                    const float C = __shfl_sync(0xffffffffu, q1.z, owner);
+                    const float tx0 = (float)((tile % gx) * TILE), ty0 = (float)((tile / gx) * TILE);
+                    keep = valid && !splat_misses_rect(cx, cy, A, B, C, thr, tx0, ty0, tx0 + (TILE - 1), ty0 + (TILE - 1));
+                }
+                const unsigned active = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int bin = tile * SUBBINS + (o_idx & (SUBBINS - 1));
+                    const unsigned peers = __match_any_sync(active, bin);
+                    const int leader = __ffs(peers) - 1;
+                    uint32_t base = 0;
+                    if (lane == leader) base = atomicAdd(&cursor[bin], (unsigned)__popc(peers));
+                    base = __shfl_sync(peers, base, leader);
+                    if (!emit_one(bin, ((uint64_t)o_depth << 32) | (uint32_t)o_idx, sub_offsets, cursor, keys, capacity,
+                                  base + __popc(peers & lanemask_lt())))
+                        overflow = true;
+                }
+            });
         }
-    });
     }  // virtual blocks
     if (overflow) atomicOr(&header[HDR_OVERFLOW], 1u);
 }
@@ -214,7 +304,7 @@ tile_sort_kernel(GeomState geom0, ImageState img0, uint64_t* keys0, uint64_t* ke
     uint64_t* keys_alt = keys_alt0 + (size_t)v * capacity;
     Splat* __restrict__ stream = stream0 + (size_t)v * capacity;
     const int tile = blockIdx.x;
-    if (threadIdx.x == 0) cursor[tile] = 0;  // leave the bin cursors clean for a (speculative) re-run
+    if (threadIdx.x < SUBBINS) cursor[tile * SUBBINS + threadIdx.x] = 0;  // clean cursors for a (speculative) re-run
     const int64_t b = min((int64_t)tile_offsets[tile], capacity);
     const int64_t e = min((int64_t)tile_offsets[tile + 1], capacity);
     const int n = (int)(e - b);

@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
     float* s_mean = smem;                          // 3 * PROJ_THREADS
     float* s_scale = s_mean + 3 * PROJ_THREADS;    // 3 * PROJ_THREADS
     float* s_sh = s_scale + 3 * PROJ_THREADS;      // 3 * M * PROJ_THREADS
+    const int keep_offset_words = PROJ_THREADS * (6 + 3 * (a.colors_precomp ? 0 : a.M));  // then 2 words per thread
     stage_floats(s_mean, a.means3D + (size_t)first * 3, n_items * 3);
     if (a.cov3D_precomp == nullptr) stage_floats(s_scale, a.scales + (size_t)first * 3, n_items * 3);
     const bool use_sh = a.colors_precomp == nullptr;
@@ -267,13 +268,22 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
         }
     }
 
+    // kept-tile bitmask of each Gaussian (bit = row-major index inside its tile rectangle), gathered from the
+    // pair-parallel walk below through shared-memory atomics; emit_kernel replays it instead of repeating the
+    // culling test.  Only rectangles of <= 64 tiles have one (the others take emit's cooperative path).
+    uint32_t* s_keep = reinterpret_cast<uint32_t*>(smem) + keep_offset_words + 2 * (threadIdx.x & ~31u);
+    s_keep[2 * (threadIdx.x & 31)] = 0u;
+    s_keep[2 * (threadIdx.x & 31) + 1] = 0u;
+    __syncwarp();
+
     // ---- bin counters: one aggregated atomic per distinct tile per warp step ----
     // With culling on, a (Gaussian, tile) pair is only counted if the splat can reach alpha >= 1/255
     // somewhere in the tile (exact: see splat_misses_rect); emit_kernel applies the identical test.
     uint32_t* counter = img.tile_counter;
+    const int warp_first_idx = first + (int)(threadIdx.x & ~31u);
     const bool cull = a.cull != 0;
     const int gx = a.gx;
-    warp_foreach_tile(n_tiles, rx0, ry0, rw, gx, [&](int tile, int owner, int, bool valid, unsigned) {
+    warp_foreach_tile(n_tiles, rx0, ry0, rw, gx, [&](int tile, int owner, int local, bool valid, unsigned) {
         bool keep = valid;
         if (cull) {
             const float cx = __shfl_sync(0xffffffffu, rec.q0.x, owner), cy = __shfl_sync(0xffffffffu, rec.q0.y, owner);
@@ -285,10 +295,17 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
         }
         const unsigned active = __ballot_sync(0xffffffffu, keep);
         if (keep) {
-            const unsigned peers = __match_any_sync(active, tile);
-            if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&counter[tile], (unsigned)__popc(peers));
+            if (local < 64) atomicOr(&s_keep[2 * owner + (local >> 5)], 1u << (local & 31));
+            // sub-bin = owner's Gaussian index % SUBBINS (the warp's lanes hold consecutive indices)
+            const int bin = tile * SUBBINS + ((warp_first_idx + owner) & (SUBBINS - 1));
+            const unsigned peers = __match_any_sync(active, bin);
+            if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&counter[bin], (unsigned)__popc(peers));
         }
     });
+    __syncwarp();
+    if (in_range)
+        geom.tile_mask[idx] = (unsigned long long)s_keep[2 * (threadIdx.x & 31)] |
+                              ((unsigned long long)s_keep[2 * (threadIdx.x & 31) + 1] << 32);
     }  // virtual blocks
 }
 
@@ -315,7 +332,7 @@ int sm_count() {
 
 cudaError_t launch_project(const ProjectArgs& a, cudaStream_t s) {
     if (a.P <= 0) return cudaSuccess;
-    const size_t smem = sizeof(float) * PROJ_THREADS * (6 + 3 * (size_t)(a.colors_precomp ? 0 : a.M));
+    const size_t smem = sizeof(float) * PROJ_THREADS * (8 + 3 * (size_t)(a.colors_precomp ? 0 : a.M));
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
