@@ -244,6 +244,12 @@ emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii0, GeomState
 
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_CHUNK = 4096;  // keys per shared-memory sort (32 KB)
+constexpr int BUCKET_BITS = 10;
+constexpr int BUCKETS = 1 << BUCKET_BITS;   // depth buckets of the per-tile bucket sort
+constexpr int BUCKET_MIN = 65;              // shorter lists: the bitonic network is already cheap
+constexpr int BUCKET_MAX = SORT_CHUNK / 2;  // the grouped copy lives in the second half of the key buffer
+constexpr int BUCKET_MAX_FILL = 48;         // largest bucket the quadratic in-bucket ranking accepts
+static_assert(BUCKETS % SORT_THREADS == 0, "bucket scan assigns BUCKETS / SORT_THREADS buckets per thread");
 
 // One compare-exchange of the bitonic network: pair index i of sub-stage (k, j).
 __device__ __forceinline__ void bitonic_cmpxchg(uint64_t* s, int i, int j, int k) {
@@ -295,6 +301,10 @@ __global__ void __launch_bounds__(SORT_THREADS)
 tile_sort_kernel(GeomState geom0, ImageState img0, uint64_t* keys0, uint64_t* keys_alt0, Splat* __restrict__ stream0,
                  int64_t capacity, size_t geom_stride, size_t img_stride) {
     __shared__ uint64_t s_keys[SORT_CHUNK];
+    __shared__ uint32_t s_cnt[BUCKETS];        // bucket histogram, then fill cursors
+    __shared__ uint32_t s_start[BUCKETS + 1];  // exclusive scan of the histogram
+    __shared__ uint32_t s_wsum[SORT_THREADS / 32];
+    __shared__ uint32_t s_misc[4];             // min depth bits, max depth bits, largest bucket
     const int v = blockIdx.y;
     const Splat* __restrict__ splat = geom0.at(v, geom_stride).splat;
     const ImageState img = img0.at(v, img_stride);
@@ -313,11 +323,93 @@ tile_sort_kernel(GeomState geom0, ImageState img0, uint64_t* keys0, uint64_t* ke
     const uint64_t* sorted;  // where the sorted keys end up (shared or global)
 
     if (n <= SORT_CHUNK) {
-        int n_pad = 2;
-        while (n_pad < n) n_pad <<= 1;
-        for (int i = threadIdx.x; i < n_pad; i += SORT_THREADS) s_keys[i] = i < n ? seg[i] : ~0ull;
-        __syncthreads();
-        bitonic_sort_smem(s_keys, n_pad);
+        bool sorted_by_buckets = false;
+        if (n >= BUCKET_MIN && n <= BUCKET_MAX) {
+            // Bucket sort: O(n) shared-memory operations instead of the bitonic network's O(n log^2 n).
+            // The depth bits (positive floats: monotone as integers) are mapped monotonically onto BUCKETS
+            // buckets spanning the tile's [min, max] depth; the keys are grouped by bucket with shared-memory
+            // atomics and each key then finds its exact rank among the (few) keys of its own bucket.  Tiles
+            // whose depths pile up in one bucket (exact depth ties) fall back to the bitonic network.
+            uint32_t lo = 0xffffffffu, hi = 0u;
+            for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+                const uint64_t k = seg[i];
+                s_keys[i] = k;
+                const uint32_t d = (uint32_t)(k >> 32);
+                lo = min(lo, d);
+                hi = max(hi, d);
+            }
+            for (int i = threadIdx.x; i < BUCKETS; i += SORT_THREADS) s_cnt[i] = 0;
+            if (threadIdx.x == 0) {
+                s_misc[0] = 0xffffffffu;
+                s_misc[1] = 0u;
+                s_misc[2] = 0u;
+            }
+            __syncthreads();
+            lo = __reduce_min_sync(0xffffffffu, lo);
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            if ((threadIdx.x & 31) == 0) {
+                atomicMin(&s_misc[0], lo);
+                atomicMax(&s_misc[1], hi);
+            }
+            __syncthreads();
+            const uint32_t dmin = s_misc[0], range = s_misc[1] - s_misc[0];
+            const int sh = max(0, (32 - __clz(range)) - BUCKET_BITS);  // (d - dmin) >> sh < BUCKETS
+            for (int i = threadIdx.x; i < n; i += SORT_THREADS)
+                atomicAdd(&s_cnt[((uint32_t)(s_keys[i] >> 32) - dmin) >> sh], 1u);
+            __syncthreads();
+            {   // exclusive scan of the bucket counts (BUCKETS / SORT_THREADS consecutive buckets per thread)
+                constexpr int PER = BUCKETS / SORT_THREADS;
+                uint32_t c[PER], sum = 0, mx = 0;
+#pragma unroll
+                for (int q = 0; q < PER; q++) {
+                    c[q] = s_cnt[threadIdx.x * PER + q];
+                    sum += c[q];
+                    mx = max(mx, c[q]);
+                }
+                const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+                const int incl = warp_incl_scan((int)sum);
+                if (lane == 31) s_wsum[wid] = (uint32_t)incl;
+                mx = __reduce_max_sync(0xffffffffu, mx);
+                if (lane == 0) atomicMax(&s_misc[2], mx);
+                __syncthreads();
+                uint32_t run = (uint32_t)incl - sum;
+                for (int w = 0; w < wid; w++) run += s_wsum[w];
+#pragma unroll
+                for (int q = 0; q < PER; q++) {
+                    s_start[threadIdx.x * PER + q] = run;
+                    s_cnt[threadIdx.x * PER + q] = 0;  // becomes the fill cursor
+                    run += c[q];
+                }
+                if (threadIdx.x == SORT_THREADS - 1) s_start[BUCKETS] = run;
+            }
+            __syncthreads();
+            if (s_misc[2] <= BUCKET_MAX_FILL) {
+                uint64_t* grouped = s_keys + BUCKET_MAX;  // second half of the key buffer
+                for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+                    const uint64_t k = s_keys[i];
+                    const uint32_t bkt = ((uint32_t)(k >> 32) - dmin) >> sh;
+                    grouped[s_start[bkt] + atomicAdd(&s_cnt[bkt], 1u)] = k;
+                }
+                __syncthreads();
+                for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+                    const uint64_t k = grouped[i];
+                    const uint32_t bkt = ((uint32_t)(k >> 32) - dmin) >> sh;
+                    const uint32_t b0 = s_start[bkt], b1 = s_start[bkt + 1];
+                    uint32_t rank = b0;
+                    for (uint32_t j = b0; j < b1; j++) rank += grouped[j] < k;
+                    s_keys[rank] = k;  // keys are unique: ranks are a permutation
+                }
+                __syncthreads();
+                sorted_by_buckets = true;
+            }
+        }
+        if (!sorted_by_buckets) {
+            int n_pad = 2;
+            while (n_pad < n) n_pad <<= 1;
+            for (int i = threadIdx.x; i < n_pad; i += SORT_THREADS) s_keys[i] = i < n ? seg[i] : ~0ull;
+            __syncthreads();
+            bitonic_sort_smem(s_keys, n_pad);
+        }
         sorted = s_keys;
     } else {
         // chunk sort in shared memory, written back in place
