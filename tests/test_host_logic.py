@@ -97,3 +97,56 @@ def test_synthetic_scene_statistics_and_camera_convention():
     for c in cams:
         v = torch.tensor([0.0, 0.0, 0.0, 1.0]) @ c["world_view_transform"]
         assert abs(v[2].item() - 1.9054) < 1e-3 and abs(v[0].item()) < 1e-4 and abs(v[1].item()) < 1e-4
+
+
+def test_round_capacity_grid():
+    from generativedensification_b200.rasterizer import round_capacity
+
+    assert round_capacity(0) == 4096 and round_capacity(4096) == 4096
+    prev = 0
+    for n in list(range(1, 20000, 37)) + [10 ** 6, 27_600_000, 2 ** 31 - 5]:
+        c = round_capacity(n)
+        assert c >= n and c >= prev                      # never below the request, monotone
+        assert c <= max(4096, int(n * 1.26))             # at most one grid step (25 %) above it
+        prev = c
+    # the grid is coarse: nearby requests share one size, so the caching allocator can reuse blocks
+    assert len({round_capacity(n) for n in range(1_000_000, 1_100_000, 1000)}) <= 2
+
+
+def test_camera_batch_packs_gdr_camera_blocks():
+    """CameraBatch.from_settings lays the per-view settings out as include/gdr.h's gdr_camera (48 floats)."""
+    from generativedensification_b200.views import CameraBatch
+
+    cams = synthetic.orbit_cameras(3, 64, 48)
+    bgs = [torch.tensor([0.1 * i, 0.2, 1.0 - 0.1 * i]) for i in range(3)]
+    st = [synthetic.settings_for(c, b, 2, torch.device("cpu"), scale_modifier=1.5) for c, b in zip(cams, bgs)]
+    cb = CameraBatch.from_settings(st)
+    assert cb.V == 3 and (cb.height, cb.width, cb.sh_degree, cb.scale_modifier) == (48, 64, 2, 1.5)
+    assert cb.cams.shape == (3, 48) and cb.cams.dtype == torch.float32
+    for i, s in enumerate(st):
+        row = cb.cams[i]
+        assert torch.equal(row[0:16], s.viewmatrix.reshape(16))
+        assert torch.equal(row[16:32], s.projmatrix.reshape(16))
+        assert torch.equal(row[32:35], s.campos)
+        assert abs(float(row[35]) - s.tanfovx) < 1e-7 and abs(float(row[36]) - s.tanfovy) < 1e-7
+        assert torch.equal(row[37:40], s.bg)
+        assert float(row[40:].abs().max()) == 0.0
+    bad = synthetic.settings_for(synthetic.orbit_cameras(2, 32, 32)[0], bgs[0], 2, torch.device("cpu"))
+    with pytest.raises(ValueError):
+        CameraBatch.from_settings(st + [bad])  # different image size in one batch
+    with pytest.raises(ValueError):
+        CameraBatch.from_settings([])
+
+
+def test_multi_view_rasterizer_validates_like_the_reference():
+    from generativedensification_b200.views import MultiViewRasterizer
+
+    st = [synthetic.settings_for(c, torch.ones(3), 1, torch.device("cpu")) for c in synthetic.orbit_cameras(2, 32, 32)]
+    r = MultiViewRasterizer(st)
+    z = torch.zeros
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=z(2, 3), means2D=z(2, 4), opacities=z(2, 1), scales=z(2, 3), rotations=z(2, 4))
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=z(2, 3), means2D=z(2, 4), opacities=z(2, 1), shs=z(2, 4, 3))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        r(means3D=z(2, 3), means2D=z(2, 4), opacities=z(2, 1), shs=z(2, 4, 3), scales=z(2, 3), rotations=z(2, 4))
