@@ -34,27 +34,16 @@ namespace gdr {
 namespace {
 
 constexpr int BLEND_THREADS = 128;  // 4 warps, each owns an 8x8 pixel region: 2 pixels (rows y and y+4) per lane
-constexpr int CHUNK = 256;
-
-// Bit w of the result is set iff the record may contribute to the 8x8 pixel region of warp w.
-// (lx, ly) = splat centre relative to the tile's first pixel.
-__device__ __forceinline__ unsigned region_mask(float lx, float ly, float4 con_o, float thr) {
-    unsigned m = 0;
-#pragma unroll
-    for (int w = 0; w < 4; w++) {
-        const float x0 = (float)((w & 1) * 8), y0 = (float)((w >> 1) * 8);
-        if (!splat_misses_rect(lx, ly, con_o.x, con_o.y, con_o.z, thr, x0, y0, x0 + 7.f, y0 + 7.f)) m |= 1u << w;
-    }
-    return m;
-}
+constexpr int WARPS = BLEND_THREADS / 32;
+constexpr int WCHUNK = 32;  // records per staged chunk: one record per lane to classify
+constexpr int STAGES = 3;   // per-warp ring depth (two chunks in flight behind the one being blended)
 
 __global__ void __launch_bounds__(BLEND_THREADS)
 blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restrict__ stream0, int64_t capacity,
                      float* __restrict__ out_color0, float* __restrict__ out_depth0, float* __restrict__ out_alpha0,
                      const Views vw) {
-    __shared__ __align__(128) Splat buf[2][CHUNK];
-    __shared__ __align__(8) uint64_t full[2];
-    __shared__ uint8_t s_mask[CHUNK];
+    __shared__ __align__(128) Splat buf[WARPS][STAGES][WCHUNK];
+    __shared__ __align__(8) uint64_t full[WARPS][STAGES];
 
     const int v = blockIdx.y;  // view of the batch
     const ImageState img = img0.at(v, vw.img_stride);
@@ -72,30 +61,39 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
     const int64_t rb = min((int64_t)tile_offsets[tile], capacity);
     const int64_t re = min((int64_t)tile_offsets[tile + 1], capacity);
     const int n = (int)(re - rb);
-    const int n_chunks = (n + CHUNK - 1) / CHUNK;
+    const int n_chunks = (n + WCHUNK - 1) / WCHUNK;
     const Splat* src = stream + rb;
 
+    // From here on the four warps of the CTA never synchronise with each other: each streams the tile's
+    // record list through its own ring and leaves as soon as its own 64 pixels are finished.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int px = tile_x * TILE + (warp & 1) * 8 + (lane & 7);
-    const int pya = tile_y * TILE + (warp >> 1) * 8 + (lane >> 3), pyb = pya + 4;
+    const int rx = tile_x * TILE + (warp & 1) * 8, ry = tile_y * TILE + (warp >> 1) * 8;  // region origin
+    const int px = rx + (lane & 7);
+    const int pya = ry + (lane >> 3), pyb = pya + 4;
     const bool inside_a = px < W && pya < H, inside_b = px < W && pyb < H;
     const float pxf = (float)px;
     const f32x2 pyf2 = pk((float)pya, (float)pyb);
-    const float tile_fx = (float)(tile_x * TILE), tile_fy = (float)(tile_y * TILE);
+    const float region_fx = (float)rx, region_fy = (float)ry;
+    uint64_t* my_full = full[warp];
+    Splat(*my_buf)[WCHUNK] = buf[warp];
 
-    if (threadIdx.x == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+    auto issue = [&](int c) {  // lane 0 only
+        const int cnt = min(WCHUNK, n - c * WCHUNK);
+        const uint32_t bytes = (uint32_t)(cnt * sizeof(Splat));
+        mbar_expect_tx(&my_full[c % STAGES], bytes);
+        bulk_g2s(&my_buf[c % STAGES][0], src + (size_t)c * WCHUNK, bytes, &my_full[c % STAGES]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < STAGES; st++) mbar_init(&my_full[st], 1);
         mbar_fence_init();
+        for (int c = 0; c < min(STAGES - 1, n_chunks); c++) issue(c);
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && n_chunks > 0) {
-        const uint32_t bytes = (uint32_t)(min(CHUNK, n) * sizeof(Splat));
-        mbar_expect_tx(&full[0], bytes);
-        bulk_g2s(&buf[0][0], src, bytes, &full[0]);
-    }
+    __syncwarp();
 
-    bool done_a = !inside_a, done_b = !inside_b;
+    // A pixel's alpha floor: 1/255 while it is live, +inf once it is finished (T would drop below 1e-4) or if it
+    // lies outside the image -- "finished" then needs no flag of its own in the per-record tests.
+    float amin_a = inside_a ? ALPHA_MIN : INFINITY, amin_b = inside_b ? ALPHA_MIN : INFINITY;
     f32x2 T2 = pk2(1.0f);
     // (the colour / depth sums stay scalar: ptxas will not accumulate an FFMA2 in place when its product
     // operand dies, and the register copies that follow cost more issue slots than the packing saves)
@@ -105,124 +103,106 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
 
     int c = 0;
     for (; c < n_chunks; c++) {
-        // prefetch the next chunk into the other buffer (its previous contents were
-        // released by the barrier at the end of the previous iteration)
-        if (threadIdx.x == 0 && c + 1 < n_chunks) {
-            const int cnt1 = min(CHUNK, n - (c + 1) * CHUNK);
-            const uint32_t bytes = (uint32_t)(cnt1 * sizeof(Splat));
-            mbar_expect_tx(&full[(c + 1) & 1], bytes);
-            bulk_g2s(&buf[(c + 1) & 1][0], src + (size_t)(c + 1) * CHUNK, bytes, &full[(c + 1) & 1]);
-        }
-        mbar_wait(&full[c & 1], (c >> 1) & 1);
-        const int cnt = min(CHUNK, n - c * CHUNK);
-        const Splat* sp = &buf[c & 1][0];
+        // every lane has finished chunk c - 1, whose ring slot is the one chunk c + STAGES - 1 lands in
+        __syncwarp();
+        if (lane == 0 && c + STAGES - 1 < n_chunks) issue(c + STAGES - 1);
+        mbar_wait(&my_full[c % STAGES], (c / STAGES) & 1);
+        const int cnt = min(WCHUNK, n - c * WCHUNK);
+        const Splat* sp = &my_buf[c % STAGES][0];
 
-        // classify: each thread tests two records against the four 8x8 regions of the tile
-#pragma unroll
-        for (int h = 0; h < CHUNK / BLEND_THREADS; h++) {
-            const int r = h * BLEND_THREADS + (int)threadIdx.x;
-            unsigned m = 0;
-            if (r < cnt) {
-                const float4 q0 = sp[r].q0;
-                m = region_mask(q0.x - tile_fx, q0.y - tile_fy, sp[r].q1, q0.z);
-            }
-            s_mask[r] = (uint8_t)m;
+        // classify: lane l tests record l of the chunk against this warp's 8x8 region (exact rectangle bound)
+        bool hit = false;
+        if (lane < cnt) {
+            const float4 q0 = sp[lane].q0;
+            const float4 q1 = sp[lane].q1;
+            hit = !splat_misses_rect(q0.x - region_fx, q0.y - region_fy, q1.x, q1.y, q1.z, q0.z, 0.f, 0.f, 7.f, 7.f);
         }
-        __syncthreads();
-
-        if (!__all_sync(0xffffffffu, done_a && done_b)) {
-            for (int k = 0; k * 32 < cnt; k++) {
-                unsigned word = __ballot_sync(0xffffffffu, (s_mask[k * 32 + lane] >> warp) & 1u);
-                while (word) {
-                    const int j = k * 32 + __ffs(word) - 1;
-                    word &= word - 1;
-                    const float4 q0 = sp[j].q0;
-                    const float4 con_o = sp[j].q1;
-                    const float dx = q0.x - pxf;
-                    const f32x2 dy2 = sub2(pk2(q0.y), pyf2);
-                    const f32x2 power2 = pair_power2(con_o, pk2(dx), dy2);
-                    float pa, pb;
-                    upk(power2, pa, pb);
-                    // a pixel takes part unless it is finished, power > 0, or alpha certainly < 1/255
-                    bool ma = !done_a && !(pa > 0.0f) && !(pa < q0.z);
-                    bool mb = !done_b && !(pb > 0.0f) && !(pb < q0.z);
-                    if (__any_sync(0xffffffffu, ma || mb)) {
-                        const f32x2 og2 = mul2(pk2(con_o.w), expf2(power2));
-                        float aa, ab;
-                        upk(og2, aa, ab);
-                        aa = min(0.99f, aa);
-                        ab = min(0.99f, ab);
-                        ma = ma && !(aa < ALPHA_MIN);
-                        mb = mb && !(ab < ALPHA_MIN);
-                        if (__any_sync(0xffffffffu, ma || mb)) {
-                            float Ta, Tb, tta, ttb;
-                            upk(T2, Ta, Tb);
-                            upk(mul2(T2, sub2(pk2(1.f), pk(aa, ab))), tta, ttb);  // test_T = T * (1 - alpha)
-                            if (ma && tta < T_MIN) {
-                                done_a = true;
-                                ma = false;
-                            }
-                            if (mb && ttb < T_MIN) {
-                                done_b = true;
-                                mb = false;
-                            }
-                            // a pixel that does not blend this record gets alpha = 0: every update below is then
-                            // the exact identity
-                            const f32x2 al2 = pk(ma ? aa : 0.f, mb ? ab : 0.f);
-                            const float4 q2 = sp[j].q2;
-                            float p0a, p0b, p1a, p1b, p2a, p2b, pda, pdb;
-                            upk(mul2(pk2(q2.x), al2), p0a, p0b);
-                            upk(mul2(pk2(q2.y), al2), p1a, p1b);
-                            upk(mul2(pk2(q2.z), al2), p2a, p2b);
-                            upk(mul2(pk2(q2.w), al2), pda, pdb);
-                            C0a = fmaf(p0a, Ta, C0a);
-                            C0b = fmaf(p0b, Tb, C0b);
-                            C1a = fmaf(p1a, Ta, C1a);
-                            C1b = fmaf(p1b, Tb, C1b);
-                            C2a = fmaf(p2a, Ta, C2a);
-                            C2b = fmaf(p2b, Tb, C2b);
-                            Da = fmaf(pda, Ta, Da);
-                            Db = fmaf(pdb, Tb, Db);
-                            fma2_acc(weight, al2, T2);
-                            T2 = pk(ma ? tta : Ta, mb ? ttb : Tb);
-                            const uint32_t pos1 = (uint32_t)(c * CHUNK + j + 1);
-                            last_a = ma ? pos1 : last_a;
-                            last_b = mb ? pos1 : last_b;
-                        }
-                    }
+        unsigned word = __ballot_sync(0xffffffffu, hit);
+        while (word) {
+            const int j = __ffs(word) - 1;
+            word &= word - 1;
+            const float4 q0 = sp[j].q0;
+            const float4 con_o = sp[j].q1;
+            const float dx = q0.x - pxf;
+            const f32x2 dy2 = sub2(pk2(q0.y), pyf2);
+            const f32x2 power2 = pair_power2(con_o, pk2(dx), dy2);
+            float pa, pb;
+            upk(power2, pa, pb);
+            const f32x2 og2 = mul2(pk2(con_o.w), expf2(power2));
+            float aa, ab;
+            upk(og2, aa, ab);
+            aa = min(0.99f, aa);
+            ab = min(0.99f, ab);
+            // a pixel blends this record unless power > 0, alpha < 1/255, or the pixel is finished
+            bool ma = !(pa > 0.0f) && !(aa < amin_a);
+            bool mb = !(pb > 0.0f) && !(ab < amin_b);
+            if (__any_sync(0xffffffffu, ma || mb)) {
+                float Ta, Tb, tta, ttb;
+                upk(T2, Ta, Tb);
+                upk(mul2(T2, sub2(pk2(1.f), pk(aa, ab))), tta, ttb);  // test_T = T * (1 - alpha)
+                if (ma && tta < T_MIN) {
+                    amin_a = INFINITY;
+                    ma = false;
                 }
-                if (__all_sync(0xffffffffu, done_a && done_b)) break;
+                if (mb && ttb < T_MIN) {
+                    amin_b = INFINITY;
+                    mb = false;
+                }
+                // a pixel that does not blend this record gets alpha = 0: every update below is then
+                // the exact identity
+                const f32x2 al2 = pk(ma ? aa : 0.f, mb ? ab : 0.f);
+                const float4 q2 = sp[j].q2;
+                float p0a, p0b, p1a, p1b, p2a, p2b, pda, pdb;
+                upk(mul2(pk2(q2.x), al2), p0a, p0b);
+                upk(mul2(pk2(q2.y), al2), p1a, p1b);
+                upk(mul2(pk2(q2.z), al2), p2a, p2b);
+                upk(mul2(pk2(q2.w), al2), pda, pdb);
+                C0a = fmaf(p0a, Ta, C0a);
+                C0b = fmaf(p0b, Tb, C0b);
+                C1a = fmaf(p1a, Ta, C1a);
+                C1b = fmaf(p1b, Tb, C1b);
+                C2a = fmaf(p2a, Ta, C2a);
+                C2b = fmaf(p2b, Tb, C2b);
+                Da = fmaf(pda, Ta, Da);
+                Db = fmaf(pdb, Tb, Db);
+                fma2_acc(weight, al2, T2);
+                T2 = pk(ma ? tta : Ta, mb ? ttb : Tb);
+                const uint32_t pos1 = (uint32_t)(c * WCHUNK + j + 1);
+                last_a = ma ? pos1 : last_a;
+                last_b = mb ? pos1 : last_b;
             }
         }
-        // everyone is finished with buf[c & 1] and s_mask; also the tile-wide early exit
-        if (__syncthreads_and(done_a && done_b)) break;
+        if (__all_sync(0xffffffffu, amin_a == INFINITY && amin_b == INFINITY)) {
+            c++;
+            break;
+        }
     }
-    // never leave with a bulk copy still in flight into our shared memory
-    if (threadIdx.x == 0 && c < n_chunks && c + 1 < n_chunks) mbar_wait(&full[(c + 1) & 1], ((c + 1) >> 1) & 1);
+    // never leave with a bulk copy still in flight into our shared memory: chunks c .. c + STAGES - 2 were issued
+    if (lane == 0)
+        for (int k = c; k < min(n_chunks, c + STAGES - 1); k++) mbar_wait(&my_full[k % STAGES], (k / STAGES) & 1);
 
     const size_t HW = (size_t)H * W;
     const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
     float Ta, Tb, wa, wb;
     upk(T2, Ta, Tb);
     upk(weight, wa, wb);
-    const float c0a = C0a, c0b = C0b, c1a = C1a, c1b = C1b, c2a = C2a, c2b = C2b, da = Da, db = Db;
     if (inside_a) {
         const size_t pid = (size_t)pya * W + px;
         n_contrib[pid] = last_a;
-        out_color[pid] = c0a + Ta * bg0;
-        out_color[HW + pid] = c1a + Ta * bg1;
-        out_color[2 * HW + pid] = c2a + Ta * bg2;
+        out_color[pid] = C0a + Ta * bg0;
+        out_color[HW + pid] = C1a + Ta * bg1;
+        out_color[2 * HW + pid] = C2a + Ta * bg2;
         out_alpha[pid] = wa;
-        out_depth[pid] = da;
+        out_depth[pid] = Da;
     }
     if (inside_b) {
         const size_t pid = (size_t)pyb * W + px;
         n_contrib[pid] = last_b;
-        out_color[pid] = c0b + Tb * bg0;
-        out_color[HW + pid] = c1b + Tb * bg1;
-        out_color[2 * HW + pid] = c2b + Tb * bg2;
+        out_color[pid] = C0b + Tb * bg0;
+        out_color[HW + pid] = C1b + Tb * bg1;
+        out_color[2 * HW + pid] = C2b + Tb * bg2;
         out_alpha[pid] = wb;
-        out_depth[pid] = db;
+        out_depth[pid] = Db;
     }
 }
 
