@@ -47,6 +47,17 @@ SIGNATURES = {
     "gdr_views_densify_scores": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gdr_topk_select": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "gdr_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
+    "gdr_surfel_state_bytes": (_i, [_i, _pi64]),
+    "gdr_surfel_stream_bytes": (_i, [_i64, _pi64]),
+    "gdr_surfel_aux_bytes": (_i, [_i, _i, _pi64]),
+    "gdr_surfel_backward_scratch_bytes": (_i, [_i, _pi64]),
+    "gdr_surfel_forward_project": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp,
+                                        _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gdr_surfel_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "gdr_surfel_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _vp]),
+    "gdr_knn3_mean_dist2": (_i, [_i, _vp, _vp, _vp]),
     "gdr_debug_unpack_geom": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gdr_debug_unpack_bins": (_i, [_i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "gdr_profile_enable": (_i, [_i]),

@@ -407,6 +407,164 @@ int gdr_mark_visible(int P, const float* means3D, const float* viewmatrix, const
     return GDR_OK;
 }
 
+// ---- 2D Gaussian-surfel path (surfel.cu) -------------------------------------------------------------
+int gdr_surfel_state_bytes(int P, int64_t* bytes) {
+    if (P < 0 || !bytes) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_surfel_state_bytes: bad arguments");
+    *bytes = (int64_t)80 * P + 256;
+    return GDR_OK;
+}
+
+int gdr_surfel_stream_bytes(int64_t capacity, int64_t* bytes) {
+    if (capacity < 0 || !bytes) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_surfel_stream_bytes: bad arguments");
+    *bytes = (int64_t)80 * capacity + 256;
+    return GDR_OK;
+}
+
+int gdr_surfel_aux_bytes(int W, int H, int64_t* bytes) {
+    if (W <= 0 || H <= 0 || !bytes) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_surfel_aux_bytes: bad arguments");
+    *bytes = (int64_t)12 * W * H + 256;
+    return GDR_OK;
+}
+
+int gdr_surfel_backward_scratch_bytes(int P, int64_t* bytes) {
+    if (P < 0 || !bytes) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_surfel_backward_scratch_bytes: bad arguments");
+    *bytes = (int64_t)sizeof(float) * 20 * P + 256;
+    return GDR_OK;
+}
+
+int gdr_surfel_forward_project(int P, int sh_degree, int M, int W, int H, const float* means3D, const float* shs,
+                               const float* colors_precomp, const float* opacities, const float* scales,
+                               int scale_stride, float scale_modifier, const float* rotations,
+                               const float* transmat_precomp, const float* viewmatrix, const float* projmatrix,
+                               const float* campos, int32_t* radii, void* geom_state, void* surfel_state,
+                               void* image_state, int32_t* num_rendered_host, void* stream) {
+    const char* who = "gdr_surfel_forward_project";
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P < 0 || W <= 0 || H <= 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
+    if (!image_state) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: image_state is NULL", who);
+    if (P > 0) {
+        if (!means3D || !opacities || !radii || !geom_state || !surfel_state || !viewmatrix || !projmatrix)
+            return fail(GDR_ERR_INVALID_ARGUMENT, "%s: a required pointer is NULL", who);
+        if (!shs && !colors_precomp) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: provide SHs or precomputed colors", who);
+        if (!colors_precomp && (!campos || M <= 0 || sh_degree < 0 || sh_degree > 3 || (sh_degree + 1) * (sh_degree + 1) > M))
+            return fail(GDR_ERR_INVALID_ARGUMENT, "%s: SH degree / coefficient count mismatch", who);
+        if (!transmat_precomp && (!scales || !rotations || scale_stride < 2))
+            return fail(GDR_ERR_INVALID_ARGUMENT, "%s: provide scales (>= 2 columns) + rotations or a precomputed homography", who);
+        if ((rotations && (((uintptr_t)rotations) & 15u)) || (((uintptr_t)surfel_state) & 15u))
+            return fail(GDR_ERR_INVALID_ARGUMENT, "%s: rotations / surfel_state must be 16-byte aligned", who);
+    }
+    gdr::ImageState img = gdr::ImageState::carve(image_state, W, H);
+    const int T = tiles_of(W, H);
+    GDR_CUDA(cudaMemsetAsync(img.header, 0, sizeof(uint32_t) * gdr::IMG_HEADER_WORDS, s), "memset(header)");
+    GDR_CUDA(cudaMemsetAsync(img.tile_counter, 0, sizeof(uint32_t) * (size_t)T * gdr::SUBBINS, s), "memset(tile_counter)");
+    const gdr::Views vw = single_view(P, W, H, viewmatrix, projmatrix, campos, nullptr, 0.f, 0.f);
+    if (P > 0) {
+        StageTimer t(GDR_STAGE_PROJECT, s);
+        GDR_CUDA(gdr::launch_surfel_project(P, sh_degree, M, W, H, means3D, shs, colors_precomp, opacities, scales,
+                                            scale_stride, scale_modifier, rotations, transmat_precomp, viewmatrix,
+                                            projmatrix, campos, radii, gdr::GeomState::carve(geom_state, (size_t)P),
+                                            surfel_state, img, s),
+                 "surfel_project");
+    }
+    {
+        StageTimer t(GDR_STAGE_TILE_SCAN, s);
+        GDR_CUDA(gdr::launch_tile_scan(T, img, vw, s), "tile_scan");
+    }
+    if (num_rendered_host)
+        GDR_CUDA(cudaMemcpyAsync(num_rendered_host, img.header + gdr::HDR_NUM_RENDERED, sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, s),
+                 "memcpy(num_rendered)");
+    return GDR_OK;
+}
+
+int gdr_surfel_forward_render(int P, int W, int H, const float* bg, const int32_t* radii, const void* geom_state,
+                              const void* surfel_state, void* image_state, void* surfel_stream, void* sort_scratch,
+                              int64_t capacity, float* out_color, float* out_allmap, void* surfel_aux, void* stream) {
+    const char* who = "gdr_surfel_forward_render";
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
+    if (!image_state || !bg || !out_color || !out_allmap || !surfel_aux)
+        return fail(GDR_ERR_INVALID_ARGUMENT, "%s: a required pointer is NULL", who);
+    if (capacity > 0 && (!surfel_stream || !sort_scratch))
+        return fail(GDR_ERR_INVALID_ARGUMENT, "%s: stream/scratch is NULL with capacity > 0", who);
+    if (P > 0 && (!geom_state || !surfel_state || !radii)) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: state is NULL", who);
+    gdr::ImageState img = gdr::ImageState::carve(image_state, W, H);
+    const gdr::Views vw = single_view(P, W, H, nullptr, nullptr, nullptr, bg, 0.f, 0.f);
+    if (P > 0 && capacity > 0) {
+        gdr::GeomState geom = gdr::GeomState::carve(const_cast<void*>(geom_state), (size_t)P);
+        uint64_t* keys = (uint64_t*)sort_scratch;
+        uint64_t* keys_alt = (uint64_t*)((char*)sort_scratch + gdr::align_up(sizeof(uint64_t) * (size_t)capacity, 256));
+        {
+            StageTimer t(GDR_STAGE_EMIT, s);
+            GDR_CUDA(gdr::launch_emit(P, W, H, radii, geom, img, keys, capacity, /*cull=*/0, vw, s), "emit");
+        }
+        {
+            StageTimer t(GDR_STAGE_TILE_SORT, s);
+            GDR_CUDA(gdr::launch_tile_sort_surfel(W, H, surfel_state, img, keys, keys_alt, surfel_stream, capacity, s),
+                     "tile_sort");
+        }
+    }
+    {
+        StageTimer t(GDR_STAGE_BLEND_FWD, s);
+        GDR_CUDA(gdr::launch_surfel_blend_forward(W, H, img, surfel_stream, (P > 0) ? capacity : 0, bg, out_color,
+                                                  out_allmap, (float*)surfel_aux, s),
+                 "surfel_blend_forward");
+    }
+    return GDR_OK;
+}
+
+int gdr_surfel_backward(int P, int sh_degree, int M, int W, int H, const float* bg, const float* means3D,
+                        const float* shs, const float* colors_precomp, const float* scales, int scale_stride,
+                        float scale_modifier, const float* rotations, const float* transmat_precomp,
+                        const float* viewmatrix, const float* projmatrix, const float* campos, const int32_t* radii,
+                        const void* geom_state, const void* surfel_state, const void* image_state,
+                        const void* surfel_stream, int64_t capacity, const float* out_allmap, const void* surfel_aux,
+                        const float* dL_dout_color, const float* dL_dout_allmap, void* backward_scratch,
+                        int means2D_cols, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                        float* dL_dmeans3D, float* dL_dtransmat, float* dL_dsh, float* dL_dscales,
+                        float* dL_drotations, void* stream) {
+    const char* who = "gdr_surfel_backward";
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
+    if (P == 0) return GDR_OK;
+    if (!means3D || !radii || !geom_state || !surfel_state || !image_state || !out_allmap || !surfel_aux ||
+        !dL_dout_color || !backward_scratch || !viewmatrix || !projmatrix || !bg)
+        return fail(GDR_ERR_INVALID_ARGUMENT, "%s: a required pointer is NULL", who);
+    if (capacity > 0 && !surfel_stream) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: surfel_stream is NULL", who);
+    if (means2D_cols != 3 && means2D_cols != 4) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: means2D_cols must be 3 or 4", who);
+    if (!transmat_precomp && (!scales || !rotations || scale_stride < 2))
+        return fail(GDR_ERR_INVALID_ARGUMENT, "%s: scales / rotations missing", who);
+    if ((rotations && (((uintptr_t)rotations) & 15u)) || (dL_drotations && (((uintptr_t)dL_drotations) & 15u)))
+        return fail(GDR_ERR_INVALID_ARGUMENT, "%s: float4 buffers must be 16-byte aligned", who);
+    if (!colors_precomp && (!shs || !campos)) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: shs / campos is NULL", who);
+    gdr::ImageState img = gdr::ImageState::carve(const_cast<void*>(image_state), W, H);
+    gdr::GeomState geom = gdr::GeomState::carve(const_cast<void*>(geom_state), (size_t)P);
+    float* accum = (float*)backward_scratch;
+    GDR_CUDA(cudaMemsetAsync(accum, 0, sizeof(float) * 20 * (size_t)P, s), "memset(accum)");
+    {
+        StageTimer t(GDR_STAGE_BLEND_BWD, s);
+        GDR_CUDA(gdr::launch_surfel_blend_backward(W, H, img, surfel_stream, capacity, bg, out_allmap,
+                                                   (const float*)surfel_aux, dL_dout_color, dL_dout_allmap, accum, s),
+                 "surfel_blend_backward");
+    }
+    {
+        StageTimer t(GDR_STAGE_GAUSS_BWD, s);
+        GDR_CUDA(gdr::launch_surfel_gauss_backward(P, sh_degree, M, W, H, means3D, shs, colors_precomp, scales,
+                                                   scale_stride, scale_modifier, rotations, transmat_precomp, viewmatrix,
+                                                   projmatrix, campos, radii, surfel_state, geom.clamped, accum,
+                                                   means2D_cols, dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D,
+                                                   dL_dtransmat, dL_dsh, dL_dscales, dL_drotations, s),
+                 "surfel_gauss_backward");
+    }
+    return GDR_OK;
+}
+
+int gdr_knn3_mean_dist2(int P, const float* points, float* out, void* stream) {
+    if (P < 0 || (P > 0 && (!points || !out))) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_knn3_mean_dist2: bad arguments");
+    GDR_CUDA(gdr::launch_knn3(P, points, out, (cudaStream_t)stream), "knn3");
+    return GDR_OK;
+}
+
 int gdr_debug_unpack_geom(int P, const void* geom_state, float* means2D, float* depths, float* conic_opacity,
                           float* rgb, float* cov3D, uint32_t* tiles_touched, uint8_t* clamped, void* stream) {
     if (P < 0 || (P > 0 && !geom_state)) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_debug_unpack_geom: bad arguments");

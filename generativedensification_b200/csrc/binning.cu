@@ -297,22 +297,25 @@ __device__ __forceinline__ int lower_bound_u64(const uint64_t* a, int n, uint64_
     return lo;
 }
 
+// RQ = 128-bit words per record: 3 for the 48-byte Splat, 5 for the 80-byte Surfel (surfel.cuh).
+template <int RQ>
 __global__ void __launch_bounds__(SORT_THREADS)
-tile_sort_kernel(GeomState geom0, ImageState img0, uint64_t* keys0, uint64_t* keys_alt0, Splat* __restrict__ stream0,
-                 int64_t capacity, size_t geom_stride, size_t img_stride) {
+tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t* keys0, uint64_t* keys_alt0,
+                 float4* __restrict__ stream0, int64_t capacity, size_t geom_stride, size_t img_stride) {
     __shared__ uint64_t s_keys[SORT_CHUNK];
     __shared__ uint32_t s_cnt[BUCKETS];        // bucket histogram, then fill cursors
     __shared__ uint32_t s_start[BUCKETS + 1];  // exclusive scan of the histogram
     __shared__ uint32_t s_wsum[SORT_THREADS / 32];
     __shared__ uint32_t s_misc[4];             // min depth bits, max depth bits, largest bucket
     const int v = blockIdx.y;
-    const Splat* __restrict__ splat = geom0.at(v, geom_stride).splat;
+    const float4* __restrict__ records =
+        reinterpret_cast<const float4*>(reinterpret_cast<const char*>(records0) + (size_t)v * geom_stride);
     const ImageState img = img0.at(v, img_stride);
     const uint32_t* __restrict__ tile_offsets = img.tile_offsets;
     uint32_t* __restrict__ cursor = img.tile_counter;
     uint64_t* keys = keys0 + (size_t)v * capacity;
     uint64_t* keys_alt = keys_alt0 + (size_t)v * capacity;
-    Splat* __restrict__ stream = stream0 + (size_t)v * capacity;
+    float4* __restrict__ stream = stream0 + (size_t)v * capacity * RQ;
     const int tile = blockIdx.x;
     if (threadIdx.x < SUBBINS) cursor[tile * SUBBINS + threadIdx.x] = 0;  // clean cursors for a (speculative) re-run
     const int64_t b = min((int64_t)tile_offsets[tile], capacity);
@@ -448,15 +451,16 @@ tile_sort_kernel(GeomState geom0, ImageState img0, uint64_t* keys0, uint64_t* ke
     }
 
     // gather the Gaussians' records into the tile's contiguous, depth-ordered stream
-    Splat* out = stream + b;
+    float4* out = stream + (size_t)b * RQ;
     for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
         const uint32_t id = (uint32_t)(sorted[i] & 0xffffffffu);
-        const float4* src4 = reinterpret_cast<const float4*>(splat + id);
-        const float4 a0 = __ldg(src4), a1 = __ldg(src4 + 1), a2 = __ldg(src4 + 2);
-        float4* dst4 = reinterpret_cast<float4*>(out + i);
-        dst4[0] = a0;
-        dst4[1] = a1;
-        dst4[2] = a2;
+        const float4* src4 = records + (size_t)id * RQ;
+        float4 w[RQ];
+#pragma unroll
+        for (int q = 0; q < RQ; q++) w[q] = __ldg(src4 + q);
+        float4* dst4 = out + (size_t)i * RQ;
+#pragma unroll
+        for (int q = 0; q < RQ; q++) dst4[q] = w[q];
     }
 }
 
@@ -484,8 +488,18 @@ cudaError_t launch_emit(int P, int W, int H, const int32_t* radii, GeomState geo
 cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint64_t* keys, uint64_t* keys_alt,
                              Splat* stream, int64_t capacity, const Views& vw, cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    tile_sort_kernel<<<dim3(gx * gy, max(1, vw.V)), SORT_THREADS, 0, s>>>(geom, img, keys, keys_alt, stream, capacity,
-                                                                          vw.geom_stride, vw.img_stride);
+    tile_sort_kernel<3><<<dim3(gx * gy, max(1, vw.V)), SORT_THREADS, 0, s>>>(
+        reinterpret_cast<const float4*>(geom.splat), img, keys, keys_alt, reinterpret_cast<float4*>(stream), capacity,
+        vw.geom_stride, vw.img_stride);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tile_sort_surfel(int W, int H, const void* surfel_records, ImageState img, uint64_t* keys,
+                                    uint64_t* keys_alt, void* surfel_stream, int64_t capacity, cudaStream_t s) {
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    tile_sort_kernel<5><<<dim3(gx * gy, 1), SORT_THREADS, 0, s>>>(reinterpret_cast<const float4*>(surfel_records), img,
+                                                                  keys, keys_alt, reinterpret_cast<float4*>(surfel_stream),
+                                                                  capacity, 0, 0);
     return cudaGetLastError();
 }
 

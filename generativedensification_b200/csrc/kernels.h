@@ -44,6 +44,10 @@ cudaError_t launch_emit(int P, int W, int H, const int32_t* radii, GeomState geo
 cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint64_t* keys, uint64_t* keys_alt,
                              Splat* stream, int64_t capacity, const Views& vw, cudaStream_t s);
 
+// The same per-tile sort with 80-byte Surfel records (surfel.cuh) gathered into the stream; single view.
+cudaError_t launch_tile_sort_surfel(int W, int H, const void* surfel_records, ImageState img, uint64_t* keys,
+                                    uint64_t* keys_alt, void* surfel_stream, int64_t capacity, cudaStream_t s);
+
 // blend_fwd.cu
 cudaError_t launch_blend_forward(int W, int H, ImageState img, const Splat* stream, int64_t capacity,
                                  float* out_color, float* out_depth, float* out_alpha, const Views& vw,
@@ -90,6 +94,34 @@ cudaError_t launch_densify_score(int V, int P, const float* accum, const uint8_t
                                  cudaStream_t s);
 cudaError_t launch_topk_select(int P, const float* score, int k, uint8_t* selected, int32_t* selected_idx,
                                int32_t* rest_idx, int32_t* counts, cudaStream_t s);
+
+// surfel.cu: the 2D Gaussian-surfel path behind the diff_surfel_rasterization-shaped module
+// (lightning/renderer_2dgs.py:224-233).  Single view; binning is shared with the 3DGS path.
+cudaError_t launch_surfel_project(int P, int sh_degree, int M, int W, int H, const float* means3D, const float* shs,
+                                  const float* colors_precomp, const float* opacities, const float* scales,
+                                  int scale_stride, float scale_modifier, const float* rotations,
+                                  const float* transmat_precomp, const float* view, const float* proj,
+                                  const float* campos, int32_t* radii, GeomState geom, void* surfel_state,
+                                  ImageState img, cudaStream_t s);
+cudaError_t launch_surfel_blend_forward(int W, int H, ImageState img, const void* stream, int64_t capacity,
+                                        const float* bg, float* out_color, float* out_allmap, float* aux,
+                                        cudaStream_t s);
+cudaError_t launch_surfel_blend_backward(int W, int H, ImageState img, const void* stream, int64_t capacity,
+                                         const float* bg, const float* out_allmap, const float* aux,
+                                         const float* dL_dcolor, const float* dL_dallmap, float* accum,
+                                         cudaStream_t s);
+cudaError_t launch_surfel_gauss_backward(int P, int sh_degree, int M, int W, int H, const float* means3D,
+                                         const float* shs, const float* colors_precomp, const float* scales,
+                                         int scale_stride, float scale_modifier, const float* rotations,
+                                         const float* transmat_precomp, const float* view, const float* proj,
+                                         const float* campos, const int32_t* radii, const void* surfel_state,
+                                         const uint8_t* clamped, const float* accum, int means2D_cols,
+                                         float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
+                                         float* dL_dtransmat, float* dL_dsh, float* dL_dscales, float* dL_drotations,
+                                         cudaStream_t s);
+
+// knn.cu: mean squared distance to the 3 nearest neighbours (simple_knn's distCUDA2)
+cudaError_t launch_knn3(int P, const float* points, float* out, cudaStream_t s);
 
 // debug.cu
 cudaError_t launch_unpack_geom(int P, GeomState geom, float* means2D, float* depths, float* conic_opacity, float* rgb,

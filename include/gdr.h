@@ -201,6 +201,59 @@ GDR_API int gdr_views_densify_scores(int V, int P, int W, int H, const gdr_camer
 GDR_API int gdr_topk_select(int P, const float* scores, int k, uint8_t* selected, int32_t* selected_idx,
                         int32_t* rest_idx, int32_t* counts, void* stream);
 
+/* ---- 2D Gaussian-surfel (2DGS) path: the diff_surfel_rasterization-shaped module -------------------------
+ * Replaces the `diff_surfel_rasterization._C` extension that lightning/renderer_2dgs.py:7-10 of the reference
+ * imports and calls at :224-233 (rasterize_gaussians -> (color, radii, allmap); allmap[7,H,W] = expected depth,
+ * alpha, view-space normal x3, median depth, depth distortion, read at :241-257).  That extension's source is NOT in
+ * the reference tree (not vendored, no submodule, no pinned version): PARITY UNPINNED.  The arithmetic is the
+ * published 2DGS algorithm (ray-splat intersection through the splat->pixel homography, sqrt(2)/2 px low-pass, 1/255 and
+ * 1e-4 cut-offs, depth-distortion accumulation); the checker is oracle/surfel_oracle.py.
+ * Same conventions as the 3DGS entry points: raw device pointers, caller-owned state, no synchronisation, transposed
+ * view / projection matrices.  geom_state / image_state / sort_scratch are the SAME opaque buffers (and sizes) as the
+ * 3DGS path -- the binning kernels are shared.  `scales` is [P, scale_stride] with scale_stride >= 2: only the two
+ * tangent scales are read (the reference's Gaussian heads carry 3).  `transmat_precomp` ([P,9] = rows Tu, Tv, Tw of the
+ * splat->pixel homography) replaces scales + rotations when non-NULL (the module's cov3D_precomp argument). */
+GDR_API int gdr_surfel_state_bytes(int P, int64_t* bytes);              /* 80-byte record per surfel, saved for backward */
+GDR_API int gdr_surfel_stream_bytes(int64_t capacity, int64_t* bytes);  /* depth-sorted per-tile record stream, saved */
+GDR_API int gdr_surfel_aux_bytes(int W, int H, int64_t* bytes);         /* per pixel: median contributor, M1, M2; saved */
+GDR_API int gdr_surfel_backward_scratch_bytes(int P, int64_t* bytes);   /* temporary: 20 floats per surfel */
+
+GDR_API int gdr_surfel_forward_project(int P, int sh_degree, int M, int W, int H,
+                        const float* means3D, const float* shs, const float* colors_precomp,
+                        const float* opacities, const float* scales, int scale_stride, float scale_modifier,
+                        const float* rotations, const float* transmat_precomp,
+                        const float* viewmatrix, const float* projmatrix, const float* campos,
+                        int32_t* radii /* out [P] */, void* geom_state, void* surfel_state, void* image_state,
+                        int32_t* num_rendered_host /* pinned host memory or NULL */, void* stream);
+
+/* out_color [3,H,W], out_allmap [7,H,W]. */
+GDR_API int gdr_surfel_forward_render(int P, int W, int H, const float* bg, const int32_t* radii,
+                        const void* geom_state, const void* surfel_state, void* image_state,
+                        void* surfel_stream, void* sort_scratch, int64_t capacity,
+                        float* out_color, float* out_allmap, void* surfel_aux, void* stream);
+
+/* dL_dout_allmap may be NULL (zero).  Any output pointer may be NULL; requested outputs are fully written.
+ * dL_dmeans2D is [P, means2D_cols] (3 or 4): columns 0:2 = the densification statistic of 2DGS (gradient w.r.t. the
+ * centre's homogeneous pixel offsets scaled to NDC), column 2 = 0 (3 columns) or columns 2:4 = the sums of the
+ * absolute per-pixel values (4 columns, the convention of the reference's 3DGS fork, backward.cu:592-594).
+ * dL_dscales is [P, scale_stride] (columns >= 2 are zero); dL_dtransmat [P,9] only with transmat_precomp. */
+GDR_API int gdr_surfel_backward(int P, int sh_degree, int M, int W, int H, const float* bg,
+                        const float* means3D, const float* shs, const float* colors_precomp,
+                        const float* scales, int scale_stride, float scale_modifier, const float* rotations,
+                        const float* transmat_precomp, const float* viewmatrix, const float* projmatrix,
+                        const float* campos, const int32_t* radii,
+                        const void* geom_state, const void* surfel_state, const void* image_state,
+                        const void* surfel_stream, int64_t capacity, const float* out_allmap, const void* surfel_aux,
+                        const float* dL_dout_color, const float* dL_dout_allmap, void* backward_scratch,
+                        int means2D_cols, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                        float* dL_dmeans3D, float* dL_dtransmat, float* dL_dsh, float* dL_dscales,
+                        float* dL_drotations, void* stream);
+
+/* out[i] = mean squared distance of points[i] to its 3 nearest neighbours (exact, brute force over shared-memory
+ * tiles) -- the quantity `simple_knn._C.distCUDA2` returns, imported by lightning/renderer_2dgs.py:11 and
+ * lightning/point_decoder/layers/head.py:7 (simple_knn is not in the reference tree either). */
+GDR_API int gdr_knn3_mean_dist2(int P, const float* points /*[P,3]*/, float* out /*[P]*/, void* stream);
+
 /* Introspection for tests: copies of the per-Gaussian state in the reference's field layout
  * (geomState.means2D / depths / conic_opacity / rgb / tiles_touched / clamped, rasterizer_impl.h:33-48).
  * Any output pointer may be NULL. */
