@@ -1,0 +1,425 @@
+// Stage 4, second generation: backward alpha blend with TWO pixels per lane.
+//
+// Same mathematics and the same two-phase pixel -> record transposition as blend_bwd.cu (see the
+// header there; replaces renderCUDA backward, RAST/cuda_rasterizer/backward.cu:415-605), reorganised
+// the way blend_fwd.cu is:
+//   * a warp owns an 8x8 pixel region, each lane the pixels (x, y) and (x, y + 4); the exponent, the
+//     exp range reduction and the whole per-pair backward recurrence run as packed FP32 pairs
+//     (FFMA2 / FMUL2 / FADD2), so the list walk, the record loads, the votes and the arithmetic are
+//     paid once per two pixels -- and an 8x8 region is visited by 0.64x as many (warp, record)
+//     pairs as the two 8x4 blocks it replaces;
+//   * the four warps of a CTA never synchronise: each streams the tile's record list back to front
+//     through its own 3-deep ring of 32-record chunks (cp.async.bulk + mbarrier), starting at ITS
+//     deepest last contributor, classifies one record per lane against its region (exact rectangle
+//     bound) and walks the set bits from the back;
+//   * phase 2 (lane = record) reads the (visit, pixel) planes with LDS.128 and accumulates the 12
+//     per-Gaussian sums over pixel PAIRS with packed instructions; the visited records' q0 / q1 are
+//     copied into the warp's scratch at visit time, so a batch survives the recycling of the chunk
+//     ring and is always flushed full (except the last).
+// A pixel that does not blend a record gets alpha = 0 and G = 0 for it: every update of its state
+// is then the exact identity and it deposits exact zeros in the planes.
+#include <stdlib.h>
+
+#include "kernels.h"
+
+namespace gdr {
+
+namespace {
+
+constexpr int B2_THREADS = 128;
+constexpr int B2_WARPS = B2_THREADS / 32;
+constexpr int WCHUNK = 32;
+constexpr int STAGES = 2;
+constexpr int BATCH = 8;             // visits gathered before one phase-2 pass
+constexpr int GROUPS = 32 / BATCH;   // phase 2: lane = (record r, pixel group g); a group is 64 / GROUPS pixels
+constexpr int ROWS_PER_GROUP = 8 / GROUPS;
+constexpr int ROW = 68;              // padded plane row (64 pixels): 16-byte aligned, conflict-free LDS.128
+
+struct WarpScratch {
+    float s[BATCH][ROW];  // G * dL/dalpha of (visit slot, pixel); pixel index = row * 8 + column of the 8x8 region
+    float w[BATCH][ROW];  // alpha * T
+    float4 dpix[64];      // (dL/dR, dL/dG, dL/dB, dL/ddepth) of the region's pixels
+    float4 rq0[BATCH];    // q0 of the visited records: x, y, reject threshold, Gaussian index
+    float4 rq1[BATCH];    // q1: conic a, b, c, opacity
+};
+
+struct Smem {
+    Splat buf[B2_WARPS][STAGES][WCHUNK];
+    WarpScratch ws[B2_WARPS];
+    uint64_t full[B2_WARPS][STAGES];
+};
+
+__device__ __forceinline__ f32x2 rcp2_normal(f32x2 x2) {  // 1 / x for x in [0.01, 1], both halves
+    float xa, xb, ra, rb;
+    upk(x2, xa, xb);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(xa));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(xb));
+    const f32x2 r2 = pk(ra, rb);
+    const f32x2 e2 = fma2(x2, r2, pk2(-1.f));
+    float ea, eb;
+    upk(e2, ea, eb);
+    return fma2(r2, pk(-ea, -eb), r2);
+}
+
+__device__ __forceinline__ float hsum(f32x2 v) {
+    float a, b;
+    upk(v, a, b);
+    return a + b;
+}
+
+template <bool FULL>
+__device__ __forceinline__ void flush_batch(WarpScratch& ws, int nb, int lane, float bx, float by, float ddelx_dx,
+                                            float ddely_dy, float* __restrict__ accum) {
+    __syncwarp();
+    const unsigned fullmask = 0xffffffffu;
+    const int r = lane & (BATCH - 1), g = lane / BATCH;
+    const float4 q0 = ws.rq0[r];
+    const float4 q1 = ws.rq1[r];
+    const float cxr = q0.x - bx;
+    f32x2 dx2[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) dx2[i] = pk(cxr - (float)(2 * i), cxr - (float)(2 * i + 1));
+    const int row0 = g * ROWS_PER_GROUP;
+    f32x2 Sx2 = pk2(0.f), Sy2 = pk2(0.f), S02 = pk2(0.f), Sxx2 = pk2(0.f), Sxy2 = pk2(0.f), Syy2 = pk2(0.f);
+    f32x2 C01 = pk2(0.f), C23 = pk2(0.f);
+    float Ax = 0.f, Ay = 0.f;
+    const f32x2 qa2 = pk2(q1.x), qb2 = pk2(q1.y), qc2 = pk2(q1.z);
+#pragma unroll
+    for (int row = 0; row < ROWS_PER_GROUP; row++) {
+        const float dy = q0.y - (by + (float)(row0 + row));
+        const f32x2 dy2 = pk2(dy);
+        const float* srow = &ws.s[r][(row0 + row) * 8];
+        const float* wrow = &ws.w[r][(row0 + row) * 8];
+        const float4* drow = &ws.dpix[(row0 + row) * 8];
+#pragma unroll
+        for (int i4 = 0; i4 < 2; i4++) {
+            const float4 s4 = *reinterpret_cast<const float4*>(srow + i4 * 4);
+            float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (FULL) w4 = *reinterpret_cast<const float4*>(wrow + i4 * 4);
+            const f32x2 sp[2] = {pk(s4.x, s4.y), pk(s4.z, s4.w)};
+            const float wa[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int col = i4 * 2 + k;  // pixel pair (2 col, 2 col + 1)
+                const f32x2 sdx = mul2(sp[k], dx2[col]);
+                const f32x2 sdy = mul2(sp[k], dy2);
+                Sx2 = add2(Sx2, sdx);
+                Sy2 = add2(Sy2, sdy);
+                float t1a, t1b, t2a, t2b;
+                upk(fma2(qb2, sdy, mul2(qa2, sdx)), t1a, t1b);
+                upk(fma2(qb2, sdx, mul2(qc2, sdy)), t2a, t2b);
+                Ax += fabsf(t1a);
+                Ax += fabsf(t1b);
+                Ay += fabsf(t2a);
+                Ay += fabsf(t2b);
+                if constexpr (FULL) {
+                    S02 = add2(S02, sp[k]);
+                    Sxx2 = fma2(sdx, dx2[col], Sxx2);
+                    Sxy2 = fma2(sdx, dy2, Sxy2);
+                    Syy2 = fma2(sdy, dy2, Syy2);
+                    const float4 dA = drow[2 * col], dB = drow[2 * col + 1];
+                    C01 = fma2(pk2(wa[2 * k]), pk(dA.x, dA.y), C01);
+                    C23 = fma2(pk2(wa[2 * k]), pk(dA.z, dA.w), C23);
+                    C01 = fma2(pk2(wa[2 * k + 1]), pk(dB.x, dB.y), C01);
+                    C23 = fma2(pk2(wa[2 * k + 1]), pk(dB.z, dB.w), C23);
+                }
+            }
+        }
+    }
+    float Sx = hsum(Sx2), Sy = hsum(Sy2);
+#pragma unroll
+    for (int d = BATCH; d < 32; d <<= 1) {
+        Sx += __shfl_xor_sync(fullmask, Sx, d);
+        Sy += __shfl_xor_sync(fullmask, Sy, d);
+        Ax += __shfl_xor_sync(fullmask, Ax, d);
+        Ay += __shfl_xor_sync(fullmask, Ay, d);
+    }
+    const float o = q1.w;
+    const float ox = o * ddelx_dx, oy = o * ddely_dy;
+    // dL/dmean2D (backward.cu:589-594): dG/ddelx = -G (a dx + b dy), dG/ddely = -G (c dy + b dx)
+    const float v0 = -ox * (q1.x * Sx + q1.y * Sy);
+    const float v1 = -oy * (q1.z * Sy + q1.y * Sx);
+    const float v2 = ox * Ax;
+    const float v3 = oy * Ay;
+    float* dst = accum + (size_t)__float_as_int(q0.w) * 12;
+    const bool live = r < nb;
+    if constexpr (FULL) {
+        float S0 = hsum(S02), Sxx = hsum(Sxx2), Sxy = hsum(Sxy2), Syy = hsum(Syy2);
+        float C0, C1, C2, C3;
+        upk(C01, C0, C1);
+        upk(C23, C2, C3);
+#pragma unroll
+        for (int d = BATCH; d < 32; d <<= 1) {
+            S0 += __shfl_xor_sync(fullmask, S0, d);
+            Sxx += __shfl_xor_sync(fullmask, Sxx, d);
+            Sxy += __shfl_xor_sync(fullmask, Sxy, d);
+            Syy += __shfl_xor_sync(fullmask, Syy, d);
+            C0 += __shfl_xor_sync(fullmask, C0, d);
+            C1 += __shfl_xor_sync(fullmask, C1, d);
+            C2 += __shfl_xor_sync(fullmask, C2, d);
+            C3 += __shfl_xor_sync(fullmask, C3, d);
+        }
+        const float mh = -0.5f * o;
+        // accumulator layout: [0..3] mean2D (x, y, |x|, |y|)  [4..7] conic a, b, c, opacity  [8..11] r, g, b, depth
+        const float comp[12] = {v0, v1, v2, v3, mh * Sxx, mh * Sxy, mh * Syy, S0, C0, C1, C2, C3};
+        constexpr int PER = 12 / GROUPS;  // components scattered by each pixel group's lanes
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < PER; k++) {
+                float e = 0.f;
+#pragma unroll
+                for (int gg = 0; gg < GROUPS; gg++)
+                    if (g == gg) e = comp[gg * PER + k];
+                if (e != 0.f) atomicAdd(dst + g * PER + k, e);
+            }
+        }
+    } else {
+        const float comp[4] = {v0, v1, v2, v3};
+        constexpr int PER = 4 / GROUPS > 0 ? 4 / GROUPS : 1;
+        if (live && g * PER < 4) {
+#pragma unroll
+            for (int k = 0; k < PER; k++) {
+                float e = 0.f;
+#pragma unroll
+                for (int gg = 0; gg < GROUPS; gg++)
+                    if (g == gg && gg * PER + k < 4) e = comp[gg * PER + k];
+                if (e != 0.f) atomicAdd(dst + g * PER + k, e);
+            }
+        }
+    }
+    __syncwarp();  // the planes may be overwritten by the next batch
+}
+
+// Everything of a (warp, record) visit that does not depend on the pixels' running state.
+struct Front {
+    float4 q0, con_o;
+    float Ga, Gb, aa, ab;
+    bool ma, mb;
+};
+
+__device__ __forceinline__ Front front(const Splat* sp, int j, int ch, float pxf, f32x2 pyf2, uint32_t last_a,
+                                       uint32_t last_b) {
+    Front f;
+    const uint32_t pos0 = (uint32_t)(ch * WCHUNK + j);
+    f.q0 = sp[j].q0;
+    f.con_o = sp[j].q1;
+    const float dx = f.q0.x - pxf;
+    const f32x2 dy2 = sub2(pk2(f.q0.y), pyf2);
+    const f32x2 power2 = pair_power2(f.con_o, pk2(dx), dy2);
+    float pa, pb;
+    upk(power2, pa, pb);
+    const f32x2 G2 = expf2(power2);
+    upk(G2, f.Ga, f.Gb);
+    upk(mul2(pk2(f.con_o.w), G2), f.aa, f.ab);
+    f.aa = min(0.99f, f.aa);
+    f.ab = min(0.99f, f.ab);
+    f.ma = (pos0 < last_a) && !(pa > 0.0f) && !(f.aa < ALPHA_MIN);
+    f.mb = (pos0 < last_b) && !(pb > 0.0f) && !(f.ab < ALPHA_MIN);
+    return f;
+}
+
+template <bool FULL, int MINB>
+__global__ void __launch_bounds__(B2_THREADS, MINB)
+blend_backward2_kernel(int P, int W, int H, int gx, ImageState img0, const Splat* __restrict__ stream0, int64_t capacity,
+                       const float* __restrict__ out_alpha0, const float* __restrict__ dL_dcolor0,
+                       const float* __restrict__ dL_ddepth0, const float* __restrict__ dL_dalpha0,
+                       float* __restrict__ accum0, const Views vw) {
+    __shared__ __align__(128) Smem sm;  // static (< 48 KB): shared-window addresses fold into the instructions
+
+    const int v = blockIdx.y;  // view of the batch
+    const ImageState img = img0.at(v, vw.img_stride);
+    const uint32_t* __restrict__ tile_offsets = img.tile_offsets;
+    const uint32_t* __restrict__ n_contrib = img.n_contrib;
+    const Splat* __restrict__ stream = stream0 + (size_t)v * capacity;
+    const float* __restrict__ bg = vw.bg + (size_t)v * vw.cam_stride;
+    const size_t vHW = (size_t)v * H * W;
+    const float* __restrict__ out_alpha = out_alpha0 + vHW;
+    const float* __restrict__ dL_dcolor = dL_dcolor0 + 3 * vHW;
+    const float* __restrict__ dL_ddepth = dL_ddepth0 ? dL_ddepth0 + vHW : nullptr;
+    const float* __restrict__ dL_dalpha = dL_dalpha0 ? dL_dalpha0 + vHW : nullptr;
+    float* __restrict__ accum = accum0 + (size_t)v * P * 12;
+
+    const int tile = (int)img.tile_order[blockIdx.x];  // heaviest tiles first
+    const int tile_x = tile % gx, tile_y = tile / gx;
+    const int64_t rb = min((int64_t)tile_offsets[tile], capacity);
+    const int64_t re = min((int64_t)tile_offsets[tile + 1], capacity);
+    const int n_all = (int)(re - rb);
+    if (n_all == 0) return;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rx = tile_x * TILE + (warp & 1) * 8, ry = tile_y * TILE + (warp >> 1) * 8;  // region origin
+    const int px = rx + (lane & 7);
+    const int pya = ry + (lane >> 3), pyb = pya + 4;
+    const bool inside_a = px < W && pya < H, inside_b = px < W && pyb < H;
+    const float pxf = (float)px;
+    const f32x2 pyf2 = pk((float)pya, (float)pyb);
+    const float region_fx = (float)rx, region_fy = (float)ry;
+    const size_t HW = (size_t)H * W;
+    const size_t pid_a = (size_t)pya * W + px, pid_b = (size_t)pyb * W + px;
+    WarpScratch& ws = sm.ws[warp];
+    uint64_t* my_full = sm.full[warp];
+    Splat(*my_buf)[WCHUNK] = sm.buf[warp];
+
+    const uint32_t last_a = inside_a ? n_contrib[pid_a] : 0u;
+    const uint32_t last_b = inside_b ? n_contrib[pid_b] : 0u;
+    const uint32_t warp_last = __reduce_max_sync(0xffffffffu, max(last_a, last_b));
+    const int n = min(n_all, (int)warp_last);  // nothing behind this warp's deepest last contributor matters to it
+    if (n == 0) return;
+    const int n_chunks = (n + WCHUNK - 1) / WCHUNK;
+    const Splat* src = stream + rb;
+
+    auto issue = [&](int it) {  // lane 0 only; iteration `it` handles chunk n_chunks - 1 - it
+        const int ch = n_chunks - 1 - it;
+        const int cnt = min(WCHUNK, n - ch * WCHUNK);
+        const uint32_t bytes = (uint32_t)(cnt * sizeof(Splat));
+        mbar_expect_tx(&my_full[it % STAGES], bytes);
+        bulk_g2s(&my_buf[it % STAGES][0], src + (size_t)ch * WCHUNK, bytes, &my_full[it % STAGES]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < STAGES; st++) mbar_init(&my_full[st], 1);
+        mbar_fence_init();
+        for (int it = 0; it < min(STAGES - 1, n_chunks); it++) issue(it);
+    }
+
+    float Tfa = 0.f, Tfb = 0.f;
+    float4 dpa4 = make_float4(0.f, 0.f, 0.f, 0.f), dpb4 = dpa4;  // (dL/dR, dL/dG, dL/dB, dL/ddepth)
+    float daa = 0.f, dab = 0.f;                                   // dL/dalpha-map
+    if (inside_a) {
+        Tfa = 1.f - out_alpha[pid_a];
+        dpa4.x = dL_dcolor[pid_a];
+        dpa4.y = dL_dcolor[HW + pid_a];
+        dpa4.z = dL_dcolor[2 * HW + pid_a];
+        if (dL_ddepth) dpa4.w = dL_ddepth[pid_a];
+        if (dL_dalpha) daa = dL_dalpha[pid_a];
+    }
+    if (inside_b) {
+        Tfb = 1.f - out_alpha[pid_b];
+        dpb4.x = dL_dcolor[pid_b];
+        dpb4.y = dL_dcolor[HW + pid_b];
+        dpb4.z = dL_dcolor[2 * HW + pid_b];
+        if (dL_ddepth) dpb4.w = dL_ddepth[pid_b];
+        if (dL_dalpha) dab = dL_dalpha[pid_b];
+    }
+    ws.dpix[lane] = dpa4;
+    ws.dpix[32 + lane] = dpb4;
+    const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
+    const float bgd_a = bg0 * dpa4.x + bg1 * dpa4.y + bg2 * dpa4.z;
+    const float bgd_b = bg0 * dpb4.x + bg1 * dpb4.y + bg2 * dpb4.z;
+    const f32x2 neg_Tf_bg2 = pk(-Tfa * bgd_a, -Tfb * bgd_b);
+    const f32x2 d0_2 = pk(dpa4.x, dpb4.x), d1_2 = pk(dpa4.y, dpb4.y), d2_2 = pk(dpa4.z, dpb4.z);
+    const f32x2 dd_2 = pk(dpa4.w, dpb4.w), da_2 = pk(daa, dab);
+    f32x2 T2 = pk(Tfa, Tfb);
+    // beta = sum_ch accum_rec[ch] * dL/dpixel[ch] of the reference (backward.cu:541-561; the recurrence is linear,
+    // so one scalar carries it), folded eagerly right after a contributor is processed
+    f32x2 beta2 = pk2(0.f), aar2 = pk2(0.f);
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    __syncwarp();
+
+    int nb = 0;  // visits gathered in the current batch (warp-uniform)
+    float* const s_lane = &ws.s[0][lane];
+    float* const w_lane = &ws.w[0][lane];
+    for (int it = 0; it < n_chunks; it++) {
+        __syncwarp();  // every lane has finished chunk it - 1, whose ring slot chunk it + STAGES - 1 lands in
+        if (lane == 0 && it + STAGES - 1 < n_chunks) issue(it + STAGES - 1);
+        mbar_wait(&my_full[it % STAGES], (it / STAGES) & 1);
+        const int ch = n_chunks - 1 - it;
+        const int cnt = min(WCHUNK, n - ch * WCHUNK);
+        const Splat* sp = &my_buf[it % STAGES][0];
+        bool hit = false;
+        if (lane < cnt) {
+            const float4 q0 = sp[lane].q0;
+            const float4 q1 = sp[lane].q1;
+            hit = !splat_misses_rect(q0.x - region_fx, q0.y - region_fy, q1.x, q1.y, q1.z, q0.z, 0.f, 0.f, 7.f, 7.f);
+        }
+        unsigned word = __ballot_sync(0xffffffffu, hit);
+        // Two visits per round: their exponent / exp / alpha tests are independent and interleave (the kernel is
+        // latency-bound at its occupancy); the per-pixel recurrences then run in list order.
+        while (word) {
+            const int j1 = 31 - __clz(word);  // back to front
+            word &= ~(1u << j1);
+            const bool two = word != 0;
+            const int j2 = two ? 31 - __clz(word) : j1;
+            word &= ~(1u << j2);
+            Front f1 = front(sp, j1, ch, pxf, pyf2, last_a, last_b);
+            Front f2 = front(sp, j2, ch, pxf, pyf2, last_a, last_b);
+            const bool any1 = __any_sync(0xffffffffu, f1.ma || f1.mb);
+            const bool any2 = two && __any_sync(0xffffffffu, f2.ma || f2.mb);
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const Front& f = k == 0 ? f1 : f2;
+                if (!(k == 0 ? any1 : any2)) continue;
+                const int j = k == 0 ? j1 : j2;
+                const f32x2 al2 = pk(f.ma ? f.aa : 0.f, f.mb ? f.ab : 0.f);
+                const f32x2 Gm2 = pk(f.ma ? f.Ga : 0.f, f.mb ? f.Gb : 0.f);
+                const float4 q2 = sp[j].q2;
+                const f32x2 inv2 = rcp2_normal(sub2(pk2(1.f), al2));  // one reciprocal serves both divisions below
+                T2 = mul2(T2, inv2);                                 // transmittance in front of this record
+                const f32x2 wv2 = mul2(al2, T2);
+                // cd = sum_ch colour[ch] * dL/dpixel[ch] (+ depth), backward.cu:549-563
+                const f32x2 cd2 =
+                    fma2(pk2(q2.w), dd_2, fma2(pk2(q2.z), d2_2, fma2(pk2(q2.y), d1_2, mul2(pk2(q2.x), d0_2))));
+                const f32x2 e2 = sub2(cd2, beta2);
+                const f32x2 one_m_aar2 = sub2(pk2(1.f), aar2);
+                f32x2 dopa2 = mul2(fma2(one_m_aar2, da_2, e2), T2);
+                dopa2 = fma2(inv2, neg_Tf_bg2, dopa2);  // backward.cu:574-577
+                const f32x2 sv2 = mul2(Gm2, dopa2);
+                beta2 = fma2(al2, e2, beta2);
+                aar2 = fma2(al2, one_m_aar2, aar2);
+                float sa, sb;
+                upk(sv2, sa, sb);
+                float* srow = s_lane + nb * ROW;
+                srow[0] = sa;
+                srow[32] = sb;
+                if constexpr (FULL) {
+                    float wa, wb;
+                    upk(wv2, wa, wb);
+                    float* wrow = w_lane + nb * ROW;
+                    wrow[0] = wa;
+                    wrow[32] = wb;
+                }
+                if (lane == 0) {
+                    ws.rq0[nb] = f.q0;
+                    ws.rq1[nb] = f.con_o;
+                }
+                if (++nb == BATCH) {
+                    flush_batch<FULL>(ws, BATCH, lane, region_fx, region_fy, ddelx_dx, ddely_dy, accum);
+                    nb = 0;
+                }
+            }
+        }
+    }
+    if (nb > 0) flush_batch<FULL>(ws, nb, lane, region_fx, region_fy, ddelx_dx, ddely_dy, accum);
+}
+
+}  // namespace
+
+cudaError_t launch_blend_backward2(int P, int W, int H, ImageState img, const Splat* stream, int64_t capacity,
+                                   const float* out_alpha, const float* dL_dcolor, const float* dL_ddepth,
+                                   const float* dL_dalpha, float* accum, int grad_mask, const Views& vw,
+                                   cudaStream_t s) {
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    const bool full = (grad_mask & 31 & ~1) != 0;  // anything besides means2D requested (bit 5 = raw-parameter mode)
+    static_assert(sizeof(Smem) <= 48 * 1024, "Smem is a static __shared__ object");
+    const dim3 grid(gx * gy, max(1, vw.V));
+    static const int minb = [] {
+        const char* e = getenv("GDR_B2_MINB");
+        return e ? atoi(e) : 4;
+    }();
+#define GDR_B2_LAUNCH(F, M)                                                                                     \
+    blend_backward2_kernel<F, M><<<grid, B2_THREADS, 0, s>>>(P, W, H, gx, img, stream, capacity, out_alpha, dL_dcolor, \
+                                                             dL_ddepth, dL_dalpha, accum, vw)
+    if (full) {
+        if (minb >= 6) GDR_B2_LAUNCH(true, 6);
+        else if (minb == 5) GDR_B2_LAUNCH(true, 5);
+        else GDR_B2_LAUNCH(true, 4);
+    } else {
+        if (minb >= 6) GDR_B2_LAUNCH(false, 6);
+        else if (minb == 5) GDR_B2_LAUNCH(false, 5);
+        else GDR_B2_LAUNCH(false, 4);
+    }
+#undef GDR_B2_LAUNCH
+    return cudaGetLastError();
+}
+
+}  // namespace gdr

@@ -59,6 +59,12 @@ cudaError_t launch_blend_backward(int P, int W, int H, ImageState img, const Spl
                                   const float* dL_dalpha, float* accum, int grad_mask, const Views& vw,
                                   cudaStream_t s);
 
+// blend_bwd2.cu: the same contract, two pixels per lane (the default; launch_blend_backward dispatches to it)
+cudaError_t launch_blend_backward2(int P, int W, int H, ImageState img, const Splat* stream, int64_t capacity,
+                                   const float* out_alpha, const float* dL_dcolor, const float* dL_ddepth,
+                                   const float* dL_dalpha, float* accum, int grad_mask, const Views& vw,
+                                   cudaStream_t s);
+
 struct GaussBackwardArgs {
     int P, sh_degree, M, W, H;
     const float* means3D;
