@@ -175,6 +175,34 @@ def build_batched_step(device, cams, up_dev, a):
     return step
 
 
+def build_surfel_step(device, cams, up_dev, a):
+    """The same step through the 2D-surfel module (diff_surfel_rasterization shape; SURVEY 8f-3, parity unpinned)."""
+    from generativedensification_b200 import surfel as SF
+
+    rasterizers = []
+    for cam in cams:
+        settings = SF.GaussianRasterizationSettings(
+            image_height=a.res, image_width=a.res, tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"],
+            bg=torch.ones(3, device=device), scale_modifier=1.0, viewmatrix=cam["world_view_transform"].to(device),
+            projmatrix=cam["full_proj_transform"].to(device), sh_degree=SH_DEGREE,
+            campos=cam["camera_center"].to(device), prefiltered=False, debug=False)
+        rasterizers.append(SF.GaussianRasterizer(raster_settings=settings))
+    Gc, Gd, Ga = up_dev
+    Gall = torch.cat([Gd, Ga, Gc, Gd, Ga], 0).contiguous()  # [7,H,W] upstream gradient of the allmap
+
+    def step(gd):
+        leaves = [gd["means3D"], gd["shs"], gd["opacities"], gd["scales"], gd["rotations"]]
+        out = None
+        for rast in rasterizers:
+            m2 = torch.zeros(gd["means3D"].shape[0], 4, device=device, requires_grad=True)
+            color, radii, allmap = rast(means3D=gd["means3D"], means2D=m2, opacities=gd["opacities"], shs=gd["shs"],
+                                        scales=gd["scales"], rotations=gd["rotations"])
+            out = torch.autograd.grad([color, allmap], [m2] + leaves, [Gc, Gall])
+        return out
+
+    return step
+
+
 def measured_traffic(kernel: str):
     """dram bytes (read + write) per launch of `kernel` from the committed ncu --set full capture, or None."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
@@ -339,6 +367,20 @@ def main():
     torch.cuda.synchronize(device)
     stages = _lib.profile_read()
     _lib.profile_enable(False)
+    # the surfel (2DGS) module on the same Gaussians, cameras and step shape, with its own stage profile
+    sstep = build_surfel_step(device, cams, up_dev, a)
+    shard.barrier()
+    surfel_ms = time_steps(lambda: sstep(gd), max(3, a.steps // 2), 3, device, flush)
+    shard.barrier()
+    surfel_ms = shard.max_over_ranks(surfel_ms, device)
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    for _ in range(3):
+        flush.zero_()
+        sstep(gd)
+    torch.cuda.synchronize(device)
+    surfel_stages = _lib.profile_read()
+    _lib.profile_enable(False)
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -402,6 +444,11 @@ def main():
                              "ms_per_step": batched_ms / a.steps,
                              "api": "MultiViewRasterizer: one launch per stage for all views (opt-in; SURVEY 8f-1)"},
                     stage_ms_per_launch={k: round(v, 5) for k, v in per_stage.items()}, stage_share=share,
+                    surfel={"value": a.views * a.gpus * max(3, a.steps // 2) / (surfel_ms * 1e-3), "unit": "views/s",
+                            "ms_per_step": surfel_ms / max(3, a.steps // 2),
+                            "stage_ms_per_launch": {k: round(ms / max(n, 1), 5) for k, (ms, n) in surfel_stages.items()},
+                            "api": "diff_surfel_rasterization-shaped module (2DGS; SURVEY 8f-3, parity unpinned), "
+                                   "same Gaussians / cameras / forward+backward step"},
                     clocks=clocks)
         if a.gpus == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a)

@@ -9,7 +9,7 @@
 //     paid once per two pixels -- and an 8x8 region is visited by 0.64x as many (warp, record)
 //     pairs as the two 8x4 blocks it replaces;
 //   * the four warps of a CTA never synchronise: each streams the tile's record list back to front
-//     through its own 3-deep ring of 32-record chunks (cp.async.bulk + mbarrier), starting at ITS
+//     through its own double-buffered ring of 32-record chunks (cp.async.bulk + mbarrier), starting at ITS
 //     deepest last contributor, classifies one record per lane against its region (exact rectangle
 //     bound) and walks the set bits from the back;
 //   * phase 2 (lane = record) reads the (visit, pixel) planes with LDS.128 and accumulates the 12
@@ -18,8 +18,6 @@
 //     ring and is always flushed full (except the last).
 // A pixel that does not blend a record gets alpha = 0 and G = 0 for it: every update of its state
 // is then the exact identity and it deposits exact zeros in the planes.
-#include <stdlib.h>
-
 #include "kernels.h"
 
 namespace gdr {
@@ -402,23 +400,14 @@ cudaError_t launch_blend_backward2(int P, int W, int H, ImageState img, const Sp
     const bool full = (grad_mask & 31 & ~1) != 0;  // anything besides means2D requested (bit 5 = raw-parameter mode)
     static_assert(sizeof(Smem) <= 48 * 1024, "Smem is a static __shared__ object");
     const dim3 grid(gx * gy, max(1, vw.V));
-    static const int minb = [] {
-        const char* e = getenv("GDR_B2_MINB");
-        return e ? atoi(e) : 4;
-    }();
-#define GDR_B2_LAUNCH(F, M)                                                                                     \
-    blend_backward2_kernel<F, M><<<grid, B2_THREADS, 0, s>>>(P, W, H, gx, img, stream, capacity, out_alpha, dL_dcolor, \
-                                                             dL_ddepth, dL_dalpha, accum, vw)
-    if (full) {
-        if (minb >= 6) GDR_B2_LAUNCH(true, 6);
-        else if (minb == 5) GDR_B2_LAUNCH(true, 5);
-        else GDR_B2_LAUNCH(true, 4);
-    } else {
-        if (minb >= 6) GDR_B2_LAUNCH(false, 6);
-        else if (minb == 5) GDR_B2_LAUNCH(false, 5);
-        else GDR_B2_LAUNCH(false, 4);
-    }
-#undef GDR_B2_LAUNCH
+    // 4 CTAs (16 warps) per SM at 128 registers: measured faster than 5 or 6 CTAs with tighter register caps --
+    // the two-visit rounds need the registers to keep both visits' independent chains in flight.
+    if (full)
+        blend_backward2_kernel<true, 4><<<grid, B2_THREADS, 0, s>>>(P, W, H, gx, img, stream, capacity, out_alpha,
+                                                                    dL_dcolor, dL_ddepth, dL_dalpha, accum, vw);
+    else
+        blend_backward2_kernel<false, 4><<<grid, B2_THREADS, 0, s>>>(P, W, H, gx, img, stream, capacity, out_alpha,
+                                                                     dL_dcolor, dL_ddepth, dL_dalpha, accum, vw);
     return cudaGetLastError();
 }
 

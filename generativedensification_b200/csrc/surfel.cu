@@ -271,37 +271,40 @@ surfel_blend_forward_kernel(int W, int H, int gx, ImageState img, const Surfel* 
         mbar_wait(&sm.full[it & 1], (it >> 1) & 1);
         const int cnt = min(SCHUNK, n - it * SCHUNK);
         const Surfel* sp = &sm.buf[it & 1][0];
-        if (!done) {
-            for (int j = 0; j < cnt; j++) {
+        // (no break / continue in this loop: with them the warp's lanes do not reconverge until the loop ends and the
+        // kernel runs ~15x slower -- ncu showed 2 active threads per instruction)
+        for (int j = 0; j < cnt; j++) {
+            if (__all_sync(0xffffffffu, done)) break;  // warp-uniform
+            PairEval e;
+            const Surfel& s = sp[j];
+            const bool hit = !done && surfel_pair(s, pxf, pyf, e);
+            if (hit) {
                 contributor = (uint32_t)(it * SCHUNK + j + 1);
-                PairEval e;
-                if (!surfel_pair(sp[j], pxf, pyf, e)) continue;
                 const float test_T = T * (1.f - e.alpha);
                 if (test_T < T_MIN) {
                     done = true;
-                    break;
+                } else {
+                    const float w = e.alpha * T;
+                    // depth distortion (paper appendix): sum_i sum_{k<i} w_i w_k (m_i - m_k)^2 in one pass
+                    const float A = 1.f - T;
+                    const float m = SURFEL_FAR / (SURFEL_FAR - SURFEL_NEAR) * (1.f - SURFEL_NEAR / e.depth);
+                    distortion += (m * m * A + M2 - 2.f * m * M1) * w;
+                    D += e.depth * w;
+                    M1 += m * w;
+                    M2 += m * m * w;
+                    if (T > 0.5f) {
+                        median_depth = e.depth;
+                        median_contributor = contributor;
+                    }
+                    N0 = fmaf(s.r4.x, w, N0);
+                    N1 = fmaf(s.r4.y, w, N1);
+                    N2 = fmaf(s.r4.z, w, N2);
+                    C0 = fmaf(s.r1.w, w, C0);
+                    C1 = fmaf(s.r2.w, w, C1);
+                    C2 = fmaf(s.r3.w, w, C2);
+                    T = test_T;
+                    last_contributor = contributor;
                 }
-                const float w = e.alpha * T;
-                // depth distortion (paper appendix): sum_i sum_{k<i} w_i w_k (m_i - m_k)^2 in one pass
-                const float A = 1.f - T;
-                const float m = SURFEL_FAR / (SURFEL_FAR - SURFEL_NEAR) * (1.f - SURFEL_NEAR / e.depth);
-                distortion += (m * m * A + M2 - 2.f * m * M1) * w;
-                D += e.depth * w;
-                M1 += m * w;
-                M2 += m * m * w;
-                if (T > 0.5f) {
-                    median_depth = e.depth;
-                    median_contributor = contributor;
-                }
-                const Surfel& s = sp[j];
-                N0 = fmaf(s.r4.x, w, N0);
-                N1 = fmaf(s.r4.y, w, N1);
-                N2 = fmaf(s.r4.z, w, N2);
-                C0 = fmaf(s.r1.w, w, C0);
-                C1 = fmaf(s.r2.w, w, C1);
-                C2 = fmaf(s.r3.w, w, C2);
-                T = test_T;
-                last_contributor = contributor;
             }
         }
         if (__syncthreads_and(done)) {  // also: everyone is finished with buf[it & 1]
