@@ -28,7 +28,10 @@ constexpr int B2_THREADS = 128;
 constexpr int B2_WARPS = B2_THREADS / 32;
 constexpr int WCHUNK = 32;
 constexpr int STAGES = 2;
-constexpr int BATCH = 8;             // visits gathered before one phase-2 pass
+#ifndef GDR_B2_BATCH
+#define GDR_B2_BATCH 16
+#endif
+constexpr int BATCH = GDR_B2_BATCH;  // visits gathered before one phase-2 pass
 constexpr int GROUPS = 32 / BATCH;   // phase 2: lane = (record r, pixel group g); a group is 64 / GROUPS pixels
 constexpr int ROWS_PER_GROUP = 8 / GROUPS;
 constexpr int ROW = 68;              // padded plane row (64 pixels): 16-byte aligned, conflict-free LDS.128
@@ -222,7 +225,8 @@ blend_backward2_kernel(int P, int W, int H, int gx, ImageState img0, const Splat
                        const float* __restrict__ out_alpha0, const float* __restrict__ dL_dcolor0,
                        const float* __restrict__ dL_ddepth0, const float* __restrict__ dL_dalpha0,
                        float* __restrict__ accum0, const Views vw) {
-    __shared__ __align__(128) Smem sm;  // static (< 48 KB): shared-window addresses fold into the instructions
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
     const int v = blockIdx.y;  // view of the batch
     const ImageState img = img0.at(v, vw.img_stride);
@@ -398,15 +402,19 @@ cudaError_t launch_blend_backward2(int P, int W, int H, ImageState img, const Sp
                                    cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const bool full = (grad_mask & 31 & ~1) != 0;  // anything besides means2D requested (bit 5 = raw-parameter mode)
-    static_assert(sizeof(Smem) <= 48 * 1024, "Smem is a static __shared__ object");
+    cudaError_t e = full ? cudaFuncSetAttribute(blend_backward2_kernel<true, 4>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem))
+                         : cudaFuncSetAttribute(blend_backward2_kernel<false, 4>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return e;
     const dim3 grid(gx * gy, max(1, vw.V));
     // 4 CTAs (16 warps) per SM at 128 registers: measured faster than 5 or 6 CTAs with tighter register caps --
     // the two-visit rounds need the registers to keep both visits' independent chains in flight.
     if (full)
-        blend_backward2_kernel<true, 4><<<grid, B2_THREADS, 0, s>>>(P, W, H, gx, img, stream, capacity, out_alpha,
+        blend_backward2_kernel<true, 4><<<grid, B2_THREADS, sizeof(Smem), s>>>(P, W, H, gx, img, stream, capacity, out_alpha,
                                                                     dL_dcolor, dL_ddepth, dL_dalpha, accum, vw);
     else
-        blend_backward2_kernel<false, 4><<<grid, B2_THREADS, 0, s>>>(P, W, H, gx, img, stream, capacity, out_alpha,
+        blend_backward2_kernel<false, 4><<<grid, B2_THREADS, sizeof(Smem), s>>>(P, W, H, gx, img, stream, capacity, out_alpha,
                                                                      dL_dcolor, dL_ddepth, dL_dalpha, accum, vw);
     return cudaGetLastError();
 }
