@@ -59,6 +59,43 @@ struct SurfelProjectArgs {
     ImageState img;
 };
 
+// Bounding box of the ellipse rho3d <= cutoff^2 of the homography T (rows Tu, Tv, Tw).
+__device__ __forceinline__ bool surfel_aabb_at(const float Tu[3], const float Tv[3], const float Tw[3], float cutoff2,
+                                               float2& centre, float2& extent, float& dist_out) {
+    const float t[3] = {cutoff2, cutoff2, -1.0f};
+    const float dist = t[0] * Tw[0] * Tw[0] + t[1] * Tw[1] * Tw[1] + t[2] * Tw[2] * Tw[2];
+    dist_out = dist;
+    if (dist == 0.0f) return false;
+    const float inv = 1.0f / dist;
+    const float f[3] = {t[0] * inv, t[1] * inv, t[2] * inv};
+    centre.x = f[0] * Tu[0] * Tw[0] + f[1] * Tu[1] * Tw[1] + f[2] * Tu[2] * Tw[2];
+    centre.y = f[0] * Tv[0] * Tw[0] + f[1] * Tv[1] * Tw[1] + f[2] * Tv[2] * Tw[2];
+    const float tx = f[0] * Tu[0] * Tu[0] + f[1] * Tu[1] * Tu[1] + f[2] * Tu[2] * Tu[2];
+    const float ty = f[0] * Tv[0] * Tv[0] + f[1] * Tv[1] * Tv[1] + f[2] * Tv[2] * Tv[2];
+    extent.x = sqrtf(fmaxf(1e-4f, centre.x * centre.x - tx));
+    extent.y = sqrtf(fmaxf(1e-4f, centre.y * centre.y - ty));
+    return true;
+}
+
+// Conservative reach of a surfel around its bounding-box centre `c`: outside the square |x - c.x|, |y - c.y| <= reach no
+// pixel can get alpha >= 1/255 from it.  alpha >= 1/255 needs rho = min(rho3d, rho2d) <= 2 ln(255 o): either the
+// low-pass disc of radius sqrt(ln(255 o)) around c, or the projected ellipse rho3d <= 2 ln(255 o), whose bounding box
+// follows from the same formula as the 3-sigma box.  +inf when the ellipse is unbounded on screen (the surfel's plane
+// passes close to the eye); -1 when the opacity is too low to ever contribute.  The blend kernels use it to let a warp
+// skip the records that cannot touch its 8x4 pixel block; the slack dwarfs every rounding error of the exact tests.
+__device__ __forceinline__ float surfel_reach(const float Tu[3], const float Tv[3], const float Tw[3], float2 c,
+                                              float opacity) {
+    if (!(opacity * 255.0f > 1.0f)) return opacity == opacity ? -1.0f : INFINITY;  // NaN opacity: never skip
+    const float rho_max = 2.0f * logf(opacity * 255.0f) + 1e-3f;
+    const float r2 = sqrtf(0.5f * rho_max);
+    float2 ce, ex;
+    float dist;
+    if (!surfel_aabb_at(Tu, Tv, Tw, rho_max, ce, ex, dist) || !(dist < 0.f)) return INFINITY;
+    const float h3 = fmaxf(fabsf(ce.x - c.x) + ex.x, fabsf(ce.y - c.y) + ex.y);
+    const float h = fmaxf(r2, h3);
+    return h * 1.001f + 0.05f;
+}
+
 // Bounding box of the 3-sigma ellipse of the homography T (rows Tu, Tv, Tw).
 __device__ __forceinline__ bool surfel_aabb(const float Tu[3], const float Tv[3], const float Tw[3], float2& centre,
                                             float2& extent) {
@@ -152,7 +189,8 @@ __global__ void __launch_bounds__(SP_THREADS) surfel_project_kernel(const Surfel
                         rec.r1 = make_float4(Tu[0], Tu[1], Tu[2], rgb.x);
                         rec.r2 = make_float4(Tv[0], Tv[1], Tv[2], rgb.y);
                         rec.r3 = make_float4(Tw[0], Tw[1], Tw[2], rgb.z);
-                        rec.r4 = make_float4(mult * normal.x, mult * normal.y, mult * normal.z, pv.z);
+                        rec.r4 = make_float4(mult * normal.x, mult * normal.y, mult * normal.z,
+                                             surfel_reach(Tu, Tv, Tw, centre, __ldg(a.opacities + idx)));
                         rx0 = x0;
                         ry0 = y0;
                         rw = x1 - x0;
@@ -166,7 +204,7 @@ __global__ void __launch_bounds__(SP_THREADS) surfel_project_kernel(const Surfel
             Splat b;
             b.q0 = make_float4(rec.r0.x, rec.r0.y, 0.f, __int_as_float(idx));
             b.q1 = make_float4(0.f, 0.f, 0.f, 0.f);
-            b.q2 = make_float4(0.f, 0.f, 0.f, rec.r4.w);
+            b.q2 = make_float4(0.f, 0.f, 0.f, pv.z);
             a.geom.splat[idx] = b;
             a.geom.tiles_touched[idx] = (uint32_t)n_tiles;
             a.geom.clamped[idx] = (uint8_t)clamp_bits;
@@ -228,6 +266,24 @@ __device__ __forceinline__ bool surfel_pair(const Surfel& s, float px, float py,
     return !(e.alpha < ALPHA_MIN);
 }
 
+// Bit i of words[k] set iff record 32 k + i of the chunk can reach the warp's 8x4 pixel block (bx .. bx+7, by .. by+3).
+__device__ __forceinline__ void classify_chunk(const Surfel* sp, int cnt, int lane, float bx, float by,
+                                               unsigned (&words)[SCHUNK / 32]) {
+#pragma unroll
+    for (int k = 0; k < SCHUNK / 32; k++) {
+        bool hit = false;
+        const int j = k * 32 + lane;
+        if (j < cnt) {
+            const float4 r0 = sp[j].r0;
+            const float reach = sp[j].r4.w;
+            const float ddx = r0.x - fminf(fmaxf(r0.x, bx), bx + 7.f);
+            const float ddy = r0.y - fminf(fmaxf(r0.y, by), by + 3.f);
+            hit = !(fabsf(ddx) > reach) && !(fabsf(ddy) > reach);
+        }
+        words[k] = __ballot_sync(0xffffffffu, hit);
+    }
+}
+
 __global__ void __launch_bounds__(SB_THREADS)
 surfel_blend_forward_kernel(int W, int H, int gx, ImageState img, const Surfel* __restrict__ stream, int64_t capacity,
                             const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_allmap,
@@ -244,6 +300,7 @@ surfel_blend_forward_kernel(int W, int H, int gx, ImageState img, const Surfel* 
     const int py = tile_y * TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
+    const float bxf = (float)(tile_x * TILE + (warp & 1) * 8), byf = (float)(tile_y * TILE + (warp >> 1) * 4);
     if (threadIdx.x == 0) {
         mbar_init(&sm.full[0], 1);
         mbar_init(&sm.full[1], 1);
@@ -271,39 +328,48 @@ surfel_blend_forward_kernel(int W, int H, int gx, ImageState img, const Surfel* 
         mbar_wait(&sm.full[it & 1], (it >> 1) & 1);
         const int cnt = min(SCHUNK, n - it * SCHUNK);
         const Surfel* sp = &sm.buf[it & 1][0];
-        // (no break / continue in this loop: with them the warp's lanes do not reconverge until the loop ends and the
-        // kernel runs ~15x slower -- ncu showed 2 active threads per instruction)
-        for (int j = 0; j < cnt; j++) {
-            if (__all_sync(0xffffffffu, done)) break;  // warp-uniform
-            PairEval e;
-            const Surfel& s = sp[j];
-            const bool hit = !done && surfel_pair(s, pxf, pyf, e);
-            if (hit) {
-                contributor = (uint32_t)(it * SCHUNK + j + 1);
-                const float test_T = T * (1.f - e.alpha);
-                if (test_T < T_MIN) {
-                    done = true;
-                } else {
-                    const float w = e.alpha * T;
-                    // depth distortion (paper appendix): sum_i sum_{k<i} w_i w_k (m_i - m_k)^2 in one pass
-                    const float A = 1.f - T;
-                    const float m = SURFEL_FAR / (SURFEL_FAR - SURFEL_NEAR) * (1.f - SURFEL_NEAR / e.depth);
-                    distortion += (m * m * A + M2 - 2.f * m * M1) * w;
-                    D += e.depth * w;
-                    M1 += m * w;
-                    M2 += m * m * w;
-                    if (T > 0.5f) {
-                        median_depth = e.depth;
-                        median_contributor = contributor;
+        // Each warp walks only the records that can reach its 8x4 block.  (The walk has no divergent break /
+        // continue: with them the lanes do not reconverge until the loop ends -- ncu showed 2 active threads per
+        // instruction and a 15x slower kernel.)
+        unsigned words[SCHUNK / 32];
+        classify_chunk(sp, cnt, lane, bxf, byf, words);
+#pragma unroll
+        for (int k = 0; k < SCHUNK / 32; k++) {
+            unsigned word = words[k];
+            while (word) {
+                if (__all_sync(0xffffffffu, done)) break;  // warp-uniform
+                const int j = k * 32 + __ffs(word) - 1;
+                word &= word - 1;
+                PairEval e;
+                const Surfel& s = sp[j];
+                const bool hit = !done && surfel_pair(s, pxf, pyf, e);
+                if (hit) {
+                    contributor = (uint32_t)(it * SCHUNK + j + 1);
+                    const float test_T = T * (1.f - e.alpha);
+                    if (test_T < T_MIN) {
+                        done = true;
+                    } else {
+                        const float w = e.alpha * T;
+                        // depth distortion (paper appendix): sum_i sum_{k<i} w_i w_k (m_i - m_k)^2 in one pass
+                        const float A = 1.f - T;
+                        const float m = SURFEL_FAR / (SURFEL_FAR - SURFEL_NEAR) * (1.f - SURFEL_NEAR / e.depth);
+                        distortion += (m * m * A + M2 - 2.f * m * M1) * w;
+                        D += e.depth * w;
+                        M1 += m * w;
+                        M2 += m * m * w;
+                        if (T > 0.5f) {
+                            median_depth = e.depth;
+                            median_contributor = contributor;
+                        }
+                        N0 = fmaf(s.r4.x, w, N0);
+                        N1 = fmaf(s.r4.y, w, N1);
+                        N2 = fmaf(s.r4.z, w, N2);
+                        C0 = fmaf(s.r1.w, w, C0);
+                        C1 = fmaf(s.r2.w, w, C1);
+                        C2 = fmaf(s.r3.w, w, C2);
+                        T = test_T;
+                        last_contributor = contributor;
                     }
-                    N0 = fmaf(s.r4.x, w, N0);
-                    N1 = fmaf(s.r4.y, w, N1);
-                    N2 = fmaf(s.r4.z, w, N2);
-                    C0 = fmaf(s.r1.w, w, C0);
-                    C1 = fmaf(s.r2.w, w, C1);
-                    C2 = fmaf(s.r3.w, w, C2);
-                    T = test_T;
-                    last_contributor = contributor;
                 }
             }
         }
@@ -364,6 +430,7 @@ surfel_blend_backward_kernel(int W, int H, int gx, ImageState img, const Surfel*
     const int py = tile_y * TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
+    const float bxf = (float)(tile_x * TILE + (warp & 1) * 8), byf = (float)(tile_y * TILE + (warp >> 1) * 4);
     const size_t HW = (size_t)H * W, pid = (size_t)py * W + px;
 
     const uint32_t last_contributor = inside ? img.n_contrib[pid] : 0u;
@@ -427,7 +494,14 @@ surfel_blend_backward_kernel(int W, int H, int gx, ImageState img, const Surfel*
         const Surfel* sp = &sm.buf[it & 1][0];
         int j_hi = cnt - 1;
         if ((uint32_t)(ch * SCHUNK + cnt) > warp_last) j_hi = (int)warp_last - ch * SCHUNK - 1;
-        for (int j = j_hi; j >= 0; j--) {
+        unsigned words[SCHUNK / 32];
+        classify_chunk(sp, j_hi + 1, lane, bxf, byf, words);  // j_hi < 0: nothing to do
+#pragma unroll
+        for (int k = SCHUNK / 32 - 1; k >= 0; k--) {
+        unsigned word = words[k];
+        while (word) {
+            const int j = k * 32 + 31 - __clz(word);  // back to front
+            word &= ~(1u << (j & 31));
             const uint32_t pos = (uint32_t)(ch * SCHUNK + j);
             const Surfel& s = sp[j];
             PairEval e;
@@ -487,6 +561,7 @@ surfel_blend_backward_kernel(int W, int H, int gx, ImageState img, const Surfel*
             const float total = warp_transpose_reduce(v, lane);
             if (lane < SURFEL_ACC && total != 0.f)
                 atomicAdd(accum + (size_t)__float_as_int(s.r0.w) * SURFEL_ACC + lane, total);
+        }
         }
         __syncthreads();  // everyone is finished with buf[it & 1]
     }

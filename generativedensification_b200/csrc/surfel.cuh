@@ -17,7 +17,7 @@ namespace gdr {
 //   r1 = {Tu.x, Tu.y, Tu.z, red}      Tu, Tv, Tw: rows of the splat -> pixel homography acting on (u, v, 1)
 //   r2 = {Tv.x, Tv.y, Tv.z, green}
 //   r3 = {Tw.x, Tw.y, Tw.z, blue}
-//   r4 = {view-space normal x, y, z (flipped towards the camera), view depth of the centre}
+//   r4 = {view-space normal x, y, z (flipped towards the camera), conservative screen-space reach in pixels}
 struct __align__(16) Surfel {
     float4 r0, r1, r2, r3, r4;
 };
