@@ -8,8 +8,9 @@
 // (tile << 32 | depth bits) of idx-major emitted pairs yields.
 //
 // B200-first structure:
-//   tile_scan   one CTA scans the per-tile bin counters filled by the project
-//               kernel -> tile_offsets (the reference's `ranges`), R.
+//   tile_scan   a cluster of 8 CTAs scans the per-tile bin counters filled by the
+//               project kernel (partial sums exchanged through distributed shared
+//               memory) -> tile_offsets (the reference's `ranges`), R.
 //   emit        one thread per Gaussian replays the kept-tile bitmask the projection
 //               kernel recorded (rectangles of <= 64 tiles: no culling test, no
 //               cooperation, the slot claims of one thread overlap in flight);
@@ -25,6 +26,8 @@
 //               in the blend kernels.
 // Compared with a global 64-bit radix sort of all R pairs (6+ passes over
 // 12 B/pair), each instance is written once as an 8-byte key and read once.
+#include <cooperative_groups.h>
+
 #include "kernels.h"
 #include "tile_iter.cuh"
 
@@ -32,30 +35,50 @@ namespace gdr {
 
 namespace {
 
-constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_CLUSTER = 8;  // CTAs (SMs) that share one view's scan through distributed shared memory
 
 static_assert(SUBBINS % 4 == 0, "tile_scan_kernel moves a tile's sub-bin counters as 128-bit words");
 constexpr int SUBQ = SUBBINS / 4;  // 128-bit words per tile
 
-// One CTA per view; thread t of chunk c owns tile c * SCAN_THREADS + t and reads / writes its SUBBINS
-// counters as aligned 128-bit words (coalesced across the CTA).  Pass 1 buckets the tiles by
-// floor(log2(count)) for the heaviest-first tile order; pass 2 is a chunked block scan with a running carry.
-__global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageState img0, size_t img_stride) {
-    const ImageState img = img0.at(blockIdx.x, img_stride);
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t bucket_count[33];  // tiles per floor(log2(count)) + 1 bucket; bucket 0 = empty tiles
+struct ScanShared {
+    uint32_t bucket_count[33];  // tiles of this CTA per floor(log2(count)) + 1 bucket; bucket 0 = empty tiles
+    uint32_t bucket_above[33];  // tiles of this CTA in heavier buckets
+    uint32_t total;             // instances in this CTA's tile range
+    uint32_t max_tile;          // largest tile of this CTA's range
+};
+
+// One CLUSTER of SCAN_CLUSTER CTAs per view (a single CTA was bound by one SM's load / store path and by the
+// chain of block-wide barriers: 15 us for 2500 tiles x 8 sub-bins).  CTA r owns the contiguous tile range
+// [r * per_cta, (r + 1) * per_cta): it sums its tiles' sub-bin counters (aligned 128-bit words), publishes its
+// total / largest tile / log2-bucket histogram in its shared memory, and after one cluster barrier every CTA reads
+// its peers' values through DSMEM to get (a) its base offset and (b) where its tiles of each bucket start in the
+// heaviest-first tile order the blend kernels use.  A second cluster barrier keeps every CTA's shared memory alive
+// until all peers have read it.
+__global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SCAN_THREADS)
+tile_scan_kernel(int T, ImageState img0, size_t img_stride) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const ImageState img = img0.at(blockIdx.y, img_stride);
+    __shared__ ScanShared sh;
+    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
     __shared__ uint32_t bucket_base[33];
-    __shared__ uint32_t s_carry, s_max;
+    __shared__ uint32_t s_carry;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid < 33) bucket_count[tid] = 0;
+    const int rank = (int)cluster.block_rank();
+    const int per_cta = (T + SCAN_CLUSTER - 1) / SCAN_CLUSTER;
+    const int t0 = min(T, rank * per_cta), t1 = min(T, t0 + per_cta);
+    if (tid < 33) sh.bucket_count[tid] = 0;
     if (tid == 0) {
+        sh.total = 0;
+        sh.max_tile = 0;
         s_carry = 0;
-        s_max = 0;
     }
     __syncthreads();
     uint4* counters = reinterpret_cast<uint4*>(img.tile_counter);
-    uint32_t lmax = 0;
-    for (int i = tid; i < T; i += SCAN_THREADS) {
+    // ---- pass 1: totals, largest tile, bucket histogram of this CTA's range ----
+    uint32_t lmax = 0, lsum = 0;
+    for (int i = t0 + tid; i < t1; i += SCAN_THREADS) {
         uint32_t c = 0;
 #pragma unroll
         for (int q = 0; q < SUBQ; q++) {
@@ -63,39 +86,75 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageSta
             c += a.x + a.y + a.z + a.w;
         }
         lmax = max(lmax, c);
-        atomicAdd(&bucket_count[c ? 32 - __clz(c) : 0], 1u);
+        lsum += c;
+        atomicAdd(&sh.bucket_count[c ? 32 - __clz(c) : 0], 1u);
     }
     lmax = __reduce_max_sync(0xffffffffu, lmax);
-    if (lane == 0) atomicMax(&s_max, lmax);
-    __syncthreads();
-    if (tid == 0) {  // heaviest bucket first: longest-processing-time-first order for the blend kernels
-        uint32_t acc = 0;
-        for (int k = 32; k >= 0; k--) {
-            bucket_base[k] = acc;
-            acc += bucket_count[k];
-        }
-        img.header[HDR_MAX_TILE] = s_max;
+    lsum = __reduce_add_sync(0xffffffffu, lsum);
+    if (lane == 0) {
+        atomicMax(&sh.max_tile, lmax);
+        atomicAdd(&sh.total, lsum);
     }
     __syncthreads();
-    for (int base = 0; base < T; base += SCAN_THREADS) {
+    if (wid == 0) {  // lane l owns bucket 32 - l: an inclusive scan from the heaviest bucket down
+        const uint32_t cnt = sh.bucket_count[32 - lane];
+        const uint32_t incl = (uint32_t)warp_incl_scan((int)cnt);
+        sh.bucket_above[32 - lane] = incl - cnt;
+        if (lane == 31) sh.bucket_above[0] = incl;
+    }
+    cluster.sync();  // every CTA's ScanShared is complete and visible cluster-wide
+    // ---- exchange through distributed shared memory ----
+    if (tid < 33) {
+        // heaviest bucket first; inside a bucket the CTAs' tiles follow each other in rank order
+        uint32_t before = 0;
+#pragma unroll
+        for (int r = 0; r < SCAN_CLUSTER; r++) {
+            const ScanShared* peer = cluster.map_shared_rank(&sh, r);
+            before += peer->bucket_above[tid];
+            if (r < rank) before += peer->bucket_count[tid];
+        }
+        bucket_base[tid] = before;
+    }
+    if (tid == 64) {
+        uint32_t base = 0, mx = 0, total = 0;
+#pragma unroll
+        for (int r = 0; r < SCAN_CLUSTER; r++) {
+            const ScanShared* peer = cluster.map_shared_rank(&sh, r);
+            const uint32_t t = peer->total;
+            if (r < rank) base += t;
+            total += t;
+            mx = max(mx, peer->max_tile);
+        }
+        s_carry = base;
+        if (rank == 0) {
+            img.header[HDR_MAX_TILE] = mx;
+            img.header[HDR_NUM_RENDERED] = total;
+            img.tile_offsets[T] = total;
+            img.sub_offsets[T * SUBBINS] = total;
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: chunked block scan of this CTA's range with a running carry ----
+    for (int base = t0; base < t1; base += SCAN_THREADS) {
         const int i = base + tid;
         uint4 a[SUBQ];
         uint32_t c = 0;
 #pragma unroll
         for (int q = 0; q < SUBQ; q++) {
-            a[q] = i < T ? counters[SUBQ * i + q] : make_uint4(0, 0, 0, 0);
+            a[q] = i < t1 ? counters[SUBQ * i + q] : make_uint4(0, 0, 0, 0);
             c += a[q].x + a[q].y + a[q].z + a[q].w;
         }
         const int incl = warp_incl_scan((int)c);
         if (lane == 31) warp_sums[wid] = (uint32_t)incl;
         __syncthreads();
-        if (wid == 0) {  // exclusive scan of the 32 warp totals
-            const uint32_t ws = warp_sums[lane];
-            warp_sums[lane] = (uint32_t)warp_incl_scan((int)ws) - ws;
+        if (wid == 0) {  // exclusive scan of the warp totals
+            const uint32_t ws = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0u;
+            const uint32_t ex = (uint32_t)warp_incl_scan((int)ws) - ws;
+            if (lane < SCAN_THREADS / 32) warp_sums[lane] = ex;
         }
         __syncthreads();
-        uint32_t run = s_carry + warp_sums[wid] + (uint32_t)incl - c;
-        if (i < T) {
+        const uint32_t run = s_carry + warp_sums[wid] + (uint32_t)incl - c;
+        if (i < t1) {
             img.tile_offsets[i] = run;
             uint4* so = reinterpret_cast<uint4*>(img.sub_offsets);
             uint32_t r = run;
@@ -116,12 +175,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageSta
         if (tid == SCAN_THREADS - 1) s_carry = run + c;  // total up to and including this chunk
         __syncthreads();
     }
-    if (tid == 0) {
-        const uint32_t total = s_carry;
-        img.header[HDR_NUM_RENDERED] = total;
-        img.tile_offsets[T] = total;
-        img.sub_offsets[T * SUBBINS] = total;
-    }
+    cluster.sync();  // no CTA leaves while a peer may still read its shared memory
 }
 
 constexpr int EMIT_THREADS = 128;
@@ -467,7 +521,7 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
 }  // namespace
 
 cudaError_t launch_tile_scan(int T, ImageState img, const Views& vw, cudaStream_t s) {
-    tile_scan_kernel<<<max(1, vw.V), SCAN_THREADS, 0, s>>>(T, img, vw.img_stride);
+    tile_scan_kernel<<<dim3(SCAN_CLUSTER, max(1, vw.V)), SCAN_THREADS, 0, s>>>(T, img, vw.img_stride);
     return cudaGetLastError();
 }
 

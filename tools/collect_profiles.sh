@@ -1,7 +1,8 @@
 #!/bin/bash
 # Run on the GPU box (under gpurun): the round's evidence set.
 #   gpurun_out/launches_rN.csv      every launch of a short bench run with its device time
-#   gpurun_out/prof_rN_all.ncu-rep  one ncu --set full capture of each of our kernels
+#   gpurun_out/prof_rN_all.ncu-rep  one ncu --set full capture of each of our 3DGS kernels
+#   gpurun_out/prof_rN_surfel.ncu-rep  the same for the surfel (2DGS) kernels
 # usage: tools/collect_profiles.sh <round-tag>
 tag=${1:-r1}
 mkdir -p gpurun_out
@@ -10,3 +11,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 120 --csv --l
 ncu --set full --clock-control none --import-source on -k regex:'project_kernel|tile_scan|emit_kernel|tile_sort|blend_|gauss_backward' \
     -s 14 -c 7 -f -o gpurun_out/prof_${tag}_all python tools/prof_step.py --views 2 > gpurun_out/ncu_${tag}_all.log 2>&1
 tail -2 gpurun_out/ncu_${tag}_all.log
+ncu --set full --clock-control none --import-source on -k regex:'surfel_' \
+    -s 4 -c 4 -f -o gpurun_out/prof_${tag}_surfel python tools/prof_surfel.py --views 2 > gpurun_out/ncu_${tag}_surfel.log 2>&1
+tail -2 gpurun_out/ncu_${tag}_surfel.log
