@@ -357,6 +357,25 @@ def main():
     shard.barrier()
     batched_ms = shard.max_over_ranks(batched_ms, device)
 
+    # ... and end to end through it (same host feed, same per-step read-back as the e2e arm above; the e2e loop
+    # left one upload in flight, which is this loop's first input)
+
+    def e2e_batched_step():
+        feeder.submit(host)
+        dev = feeder.take()
+        dev = {k: v.requires_grad_(True) for k, v in dev.items()}
+        grads = bstep(dev)
+        res = torch.stack([grads[0][:, 2:4].sum(), grads[1].abs().sum()])
+        result_host.copy_(res, non_blocking=True)
+        feeder.release()
+        torch.cuda.current_stream(device).synchronize()
+        return float(result_host[0])
+
+    shard.barrier()
+    e2e_batched_ms = time_steps(e2e_batched_step, a.steps, max(3, a.warmup // 2), device, flush)
+    shard.barrier()
+    e2e_batched_ms = shard.max_over_ranks(e2e_batched_ms, device)
+
     # per-stage device time of our kernels (same steps, events around every launch)
     _lib.profile_enable(True)
     _lib.profile_read()
@@ -442,7 +461,10 @@ def main():
                               "pair_evals_per_s": pairs_per_view * 2 * views_per_s / a.gpus},
                     batched={"value": a.views * a.gpus * a.steps / (batched_ms * 1e-3), "unit": "views/s",
                              "ms_per_step": batched_ms / a.steps,
-                             "api": "MultiViewRasterizer: one launch per stage for all views (opt-in; SURVEY 8f-1)"},
+                             "e2e_value": a.views * a.gpus * a.steps / (e2e_batched_ms * 1e-3),
+                             "e2e_ms_per_step": e2e_batched_ms / a.steps,
+                             "api": "MultiViewRasterizer: one launch per stage for all views (opt-in; SURVEY 8f-1); "
+                                    "e2e_value = the same host-fed, read-back-every-step loop as `e2e`"},
                     stage_ms_per_launch={k: round(v, 5) for k, v in per_stage.items()}, stage_share=share,
                     surfel={"value": a.views * a.gpus * max(3, a.steps // 2) / (surfel_ms * 1e-3), "unit": "views/s",
                             "ms_per_step": surfel_ms / max(3, a.steps // 2),

@@ -76,22 +76,28 @@ __device__ __forceinline__ void flush_batch(WarpScratch& ws, int nb, int lane, f
     const int r = lane & (BATCH - 1), g = lane / BATCH;
     const float4 q0 = ws.rq0[r];
     const float4 q1 = ws.rq1[r];
-    const float cxr = q0.x - bx;
-    f32x2 dx2[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) dx2[i] = pk(cxr - (float)(2 * i), cxr - (float)(2 * i + 1));
+    // The six geometry-weighted sums of s (S0, Sx, Sy, Sxx, Sxy, Syy with dx = cx - column, dy = cy - row) are
+    // assembled from record-independent moments of s over the pixels (sum s, s col, s row, s col^2, s col row,
+    // s row^2): three packed operations per pixel pair instead of eight.  The |.| sums do not separate; they
+    // use u = a dx + b dy and v = c dy + b dx evaluated per pixel pair from one base value per row.
+    const float cxr = q0.x - bx, cyr = q0.y - by;
+    const f32x2 col2[4] = {pk(0.f, 1.f), pk(2.f, 3.f), pk(4.f, 5.f), pk(6.f, 7.f)};
+    const f32x2 colsq2[4] = {pk(0.f, 1.f), pk(4.f, 9.f), pk(16.f, 25.f), pk(36.f, 49.f)};
     const int row0 = g * ROWS_PER_GROUP;
-    f32x2 Sx2 = pk2(0.f), Sy2 = pk2(0.f), S02 = pk2(0.f), Sxx2 = pk2(0.f), Sxy2 = pk2(0.f), Syy2 = pk2(0.f);
-    f32x2 C01 = pk2(0.f), C23 = pk2(0.f);
+    f32x2 Mcc2 = pk2(0.f), C01 = pk2(0.f), C23 = pk2(0.f);
+    float M0 = 0.f, Mc = 0.f, Mr = 0.f, Mrr = 0.f, Mcr = 0.f;
     float Ax = 0.f, Ay = 0.f;
-    const f32x2 qa2 = pk2(q1.x), qb2 = pk2(q1.y), qc2 = pk2(q1.z);
+    const f32x2 na2 = pk2(-q1.x), nb2 = pk2(-q1.y);
 #pragma unroll
     for (int row = 0; row < ROWS_PER_GROUP; row++) {
-        const float dy = q0.y - (by + (float)(row0 + row));
-        const f32x2 dy2 = pk2(dy);
+        const float rowf = (float)(row0 + row);
+        const float dy = cyr - rowf;
+        const f32x2 ub2 = pk2(fmaf(q1.x, cxr, q1.y * dy));  // u at column 0; u(col) = ub - a col
+        const f32x2 vb2 = pk2(fmaf(q1.z, dy, q1.y * cxr));  // v at column 0; v(col) = vb - b col
         const float* srow = &ws.s[r][(row0 + row) * 8];
         const float* wrow = &ws.w[r][(row0 + row) * 8];
         const float4* drow = &ws.dpix[(row0 + row) * 8];
+        f32x2 rM02 = pk2(0.f), rMc2 = pk2(0.f);
 #pragma unroll
         for (int i4 = 0; i4 < 2; i4++) {
             const float4 s4 = *reinterpret_cast<const float4*>(srow + i4 * 4);
@@ -102,22 +108,17 @@ __device__ __forceinline__ void flush_batch(WarpScratch& ws, int nb, int lane, f
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 const int col = i4 * 2 + k;  // pixel pair (2 col, 2 col + 1)
-                const f32x2 sdx = mul2(sp[k], dx2[col]);
-                const f32x2 sdy = mul2(sp[k], dy2);
-                Sx2 = add2(Sx2, sdx);
-                Sy2 = add2(Sy2, sdy);
+                rM02 = add2(rM02, sp[k]);
+                rMc2 = fma2(sp[k], col2[col], rMc2);
                 float t1a, t1b, t2a, t2b;
-                upk(fma2(qb2, sdy, mul2(qa2, sdx)), t1a, t1b);
-                upk(fma2(qb2, sdx, mul2(qc2, sdy)), t2a, t2b);
+                upk(mul2(sp[k], fma2(na2, col2[col], ub2)), t1a, t1b);
+                upk(mul2(sp[k], fma2(nb2, col2[col], vb2)), t2a, t2b);
                 Ax += fabsf(t1a);
                 Ax += fabsf(t1b);
                 Ay += fabsf(t2a);
                 Ay += fabsf(t2b);
                 if constexpr (FULL) {
-                    S02 = add2(S02, sp[k]);
-                    Sxx2 = fma2(sdx, dx2[col], Sxx2);
-                    Sxy2 = fma2(sdx, dy2, Sxy2);
-                    Syy2 = fma2(sdy, dy2, Syy2);
+                    Mcc2 = fma2(sp[k], colsq2[col], Mcc2);
                     const float4 dA = drow[2 * col], dB = drow[2 * col + 1];
                     C01 = fma2(pk2(wa[2 * k]), pk(dA.x, dA.y), C01);
                     C23 = fma2(pk2(wa[2 * k]), pk(dA.z, dA.w), C23);
@@ -126,8 +127,24 @@ __device__ __forceinline__ void flush_batch(WarpScratch& ws, int nb, int lane, f
                 }
             }
         }
+        const float m0 = hsum(rM02), mc = hsum(rMc2);
+        M0 += m0;
+        Mc += mc;
+        Mr = fmaf(rowf, m0, Mr);
+        if constexpr (FULL) {
+            Mrr = fmaf(rowf * rowf, m0, Mrr);
+            Mcr = fmaf(rowf, mc, Mcr);
+        }
     }
-    float Sx = hsum(Sx2), Sy = hsum(Sy2);
+    float Sx = fmaf(cxr, M0, -Mc), Sy = fmaf(cyr, M0, -Mr);
+    f32x2 S02 = pk(M0, 0.f);
+    f32x2 Sxx2 = pk2(0.f), Sxy2 = pk2(0.f), Syy2 = pk2(0.f);
+    if constexpr (FULL) {
+        const float Mcc = hsum(Mcc2);
+        Sxx2 = pk(fmaf(cxr, fmaf(cxr, M0, -2.f * Mc), Mcc), 0.f);
+        Sxy2 = pk(fmaf(cxr, fmaf(cyr, M0, -Mr), fmaf(-cyr, Mc, Mcr)), 0.f);
+        Syy2 = pk(fmaf(cyr, fmaf(cyr, M0, -2.f * Mr), Mrr), 0.f);
+    }
 #pragma unroll
     for (int d = BATCH; d < 32; d <<= 1) {
         Sx += __shfl_xor_sync(fullmask, Sx, d);
