@@ -206,7 +206,7 @@ int render_impl(const char* who, const gdr::Views& vw, int P, int W, int H, cons
         const size_t total = (size_t)capacity * (size_t)vw.V;
         uint64_t* keys = (uint64_t*)sort_scratch;
         uint64_t* keys_alt = (uint64_t*)((char*)sort_scratch + gdr::align_up(sizeof(uint64_t) * total, 256));
-        // the emit cursors are zero here: tile_scan zeroes them and tile_sort re-zeroes them after use
+        // the emit cursors sit at their sub-bin offsets here: tile_scan sets them and tile_sort restores them after use
         {
             StageTimer t(GDR_STAGE_EMIT, s);
             GDR_CUDA(gdr::launch_emit(P, W, H, radii, geom, img, keys, capacity, (flags & GDR_FLAG_NO_TILE_CULL) ? 0 : 1,

@@ -167,7 +167,7 @@ tile_scan_kernel(int T, ImageState img0, size_t img_stride) {
                 o.w = o.z + a[q].z;
                 r = o.w + a[q].w;
                 so[SUBQ * i + q] = o;
-                counters[SUBQ * i + q] = make_uint4(0, 0, 0, 0);  // the counters become the emit cursors
+                counters[SUBQ * i + q] = o;  // the counters become the emit cursors: they start at the sub-bin's offset
             }
             img.tile_order[atomicAdd(&bucket_base[c ? 32 - __clz(c) : 0], 1u)] = (uint32_t)i;
         }
@@ -180,12 +180,11 @@ tile_scan_kernel(int T, ImageState img0, size_t img_stride) {
 
 constexpr int EMIT_THREADS = 128;
 
-// One instance: claim a slot of the tile's segment and write the key (depth bits << 32 | Gaussian index).
-__device__ __forceinline__ bool emit_one(int bin, uint64_t key, const uint32_t* __restrict__ sub_offsets,
-                                         uint32_t* __restrict__ cursor, uint64_t* __restrict__ keys, int64_t capacity,
-                                         uint32_t claim_base) {
-    const uint64_t pos = (uint64_t)__ldg(&sub_offsets[bin]) + claim_base;
-    if ((int64_t)pos < capacity && pos < (uint64_t)__ldg(&sub_offsets[bin + 1])) {
+// One instance: write the key (depth bits << 32 | Gaussian index) into the claimed slot.  The cursors start at
+// their sub-bin's offset (tile_scan), so a claim IS the position in the key array; the count pass and this pass
+// replay the same kept-tile decisions, so a claim can only leave its segment by exceeding `capacity`.
+__device__ __forceinline__ bool emit_one(uint64_t key, uint64_t* __restrict__ keys, int64_t capacity, uint32_t pos) {
+    if ((int64_t)pos < capacity) {
         keys[pos] = key;
         return true;
     }
@@ -200,7 +199,6 @@ emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii0, GeomState
     const GeomState geom = geom0.at(v, geom_stride);
     const Splat* __restrict__ splat = geom.splat;
     const ImageState img = img0.at(v, img_stride);
-    const uint32_t* __restrict__ sub_offsets = img.sub_offsets;
     uint32_t* __restrict__ cursor = img.tile_counter;
     uint32_t* __restrict__ header = img.header;
     uint64_t* __restrict__ keys = keys0 + (size_t)v * capacity;
@@ -233,7 +231,7 @@ emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii0, GeomState
             const uint32_t inv_w = (65536u + (uint32_t)w - 1u) / (uint32_t)w;  // local / w for local < 64, w <= 64
             while (m) {
                 int bins[4];  // sub-bin ids: tile * SUBBINS + idx % SUBBINS
-                uint32_t base[4], lo[4], hi[4];
+                uint32_t base[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     bins[u] = -1;
@@ -242,20 +240,12 @@ emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii0, GeomState
                         m &= m - 1;
                         const int row = (int)(((uint32_t)local * inv_w) >> 16);
                         bins[u] = ((y0 + row) * gx + x0 + (local - row * w)) * SUBBINS + (idx & (SUBBINS - 1));
-                        lo[u] = __ldg(&sub_offsets[bins[u]]);
-                        hi[u] = __ldg(&sub_offsets[bins[u] + 1]);
                         base[u] = atomicAdd(&cursor[bins[u]], 1u);
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    if (bins[u] >= 0) {
-                        const uint64_t pos = (uint64_t)lo[u] + base[u];
-                        if ((int64_t)pos < capacity && pos < (uint64_t)hi[u])
-                            keys[pos] = key;
-                        else
-                            overflow = true;
-                    }
+                    if (bins[u] >= 0 && !emit_one(key, keys, capacity, base[u])) overflow = true;
                 }
             }
             n = 0;  // done; takes no part in the cooperative walk below
@@ -286,7 +276,7 @@ emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii0, GeomState
                     uint32_t base = 0;
                     if (lane == leader) base = atomicAdd(&cursor[bin], (unsigned)__popc(peers));
                     base = __shfl_sync(peers, base, leader);
-                    if (!emit_one(bin, ((uint64_t)o_depth << 32) | (uint32_t)o_idx, sub_offsets, cursor, keys, capacity,
+                    if (!emit_one(((uint64_t)o_depth << 32) | (uint32_t)o_idx, keys, capacity,
                                   base + __popc(peers & lanemask_lt())))
                         overflow = true;
                 }
@@ -371,7 +361,8 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
     uint64_t* keys_alt = keys_alt0 + (size_t)v * capacity;
     float4* __restrict__ stream = stream0 + (size_t)v * capacity * RQ;
     const int tile = blockIdx.x;
-    if (threadIdx.x < SUBBINS) cursor[tile * SUBBINS + threadIdx.x] = 0;  // clean cursors for a (speculative) re-run
+    if (threadIdx.x < SUBBINS)  // cursors back at their offsets for a (speculative) re-run
+        cursor[tile * SUBBINS + threadIdx.x] = img.sub_offsets[tile * SUBBINS + threadIdx.x];
     const int64_t b = min((int64_t)tile_offsets[tile], capacity);
     const int64_t e = min((int64_t)tile_offsets[tile + 1], capacity);
     const int n = (int)(e - b);
