@@ -97,7 +97,7 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
     f32x2 T2 = pk2(1.0f);
     // (the colour / depth sums stay scalar: ptxas will not accumulate an FFMA2 in place when its product
     // operand dies, and the register copies that follow cost more issue slots than the packing saves)
-    f32x2 C0_2 = pk2(0.f), C1_2 = pk2(0.f), C2_2 = pk2(0.f), D_2 = pk2(0.f);
+    float C0a = 0.f, C0b = 0.f, C1a = 0.f, C1b = 0.f, C2a = 0.f, C2b = 0.f, Da = 0.f, Db = 0.f;
     f32x2 weight = pk2(0.f);
     uint32_t last_a = 0, last_b = 0;
 
@@ -152,10 +152,19 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
                 // the exact identity
                 const f32x2 al2 = pk(ma ? aa : 0.f, mb ? ab : 0.f);
                 const float4 q2 = sp[j].q2;
-                fma2_acc(C0_2, mul2(pk2(q2.x), al2), T2);
-                fma2_acc(C1_2, mul2(pk2(q2.y), al2), T2);
-                fma2_acc(C2_2, mul2(pk2(q2.z), al2), T2);
-                fma2_acc(D_2, mul2(pk2(q2.w), al2), T2);
+                float p0a, p0b, p1a, p1b, p2a, p2b, pda, pdb;
+                upk(mul2(pk2(q2.x), al2), p0a, p0b);
+                upk(mul2(pk2(q2.y), al2), p1a, p1b);
+                upk(mul2(pk2(q2.z), al2), p2a, p2b);
+                upk(mul2(pk2(q2.w), al2), pda, pdb);
+                C0a = fmaf(p0a, Ta, C0a);
+                C0b = fmaf(p0b, Tb, C0b);
+                C1a = fmaf(p1a, Ta, C1a);
+                C1b = fmaf(p1b, Tb, C1b);
+                C2a = fmaf(p2a, Ta, C2a);
+                C2b = fmaf(p2b, Tb, C2b);
+                Da = fmaf(pda, Ta, Da);
+                Db = fmaf(pdb, Tb, Db);
                 fma2_acc(weight, al2, T2);
                 T2 = pk(ma ? tta : Ta, mb ? ttb : Tb);
                 const uint32_t pos1 = (uint32_t)(c * WCHUNK + j + 1);
@@ -174,13 +183,9 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
 
     const size_t HW = (size_t)H * W;
     const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
-    float Ta, Tb, wa, wb, C0a, C0b, C1a, C1b, C2a, C2b, Da, Db;
+    float Ta, Tb, wa, wb;
     upk(T2, Ta, Tb);
     upk(weight, wa, wb);
-    upk(C0_2, C0a, C0b);
-    upk(C1_2, C1a, C1b);
-    upk(C2_2, C2a, C2b);
-    upk(D_2, Da, Db);
     if (inside_a) {
         const size_t pid = (size_t)pya * W + px;
         n_contrib[pid] = last_a;

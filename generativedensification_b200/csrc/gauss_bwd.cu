@@ -76,13 +76,42 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
     const bool visible = a.radii[(size_t)vi * a.P + idx] > 0;
     const GeomState geom = a.geom.at(vi, a.vw.geom_stride);
     const int M = a.M;
+    // Every per-Gaussian input is fetched here, in ONE round trip with the accumulator loads above: the output
+    // stores below may alias the inputs as far as the compiler knows, so it would issue these loads only after
+    // the stores (which wait for the accumulators) -- two serialized round trips in a latency-bound kernel.
+    const float3 mean = make_float3(__ldg(a.means3D + (size_t)idx * 3), __ldg(a.means3D + (size_t)idx * 3 + 1),
+                                    __ldg(a.means3D + (size_t)idx * 3 + 2));
+    float cov3D[6];
+    {
+        const float2* c2 = reinterpret_cast<const float2*>(
+            a.cov3D_precomp ? a.cov3D_precomp + (size_t)idx * 6 : geom.cov3D + (size_t)idx * 6);
+        const float2 c0 = c2[0], c1 = c2[1], c2v = c2[2];
+        cov3D[0] = c0.x; cov3D[1] = c0.y; cov3D[2] = c1.x; cov3D[3] = c1.y; cov3D[4] = c2v.x; cov3D[5] = c2v.y;
+    }
+    float4 q_in = make_float4(1.f, 0.f, 0.f, 0.f);
+    float3 sc_in = make_float3(0.f, 0.f, 0.f);
+    const bool want_scale_rot = a.scales != nullptr && (a.dL_dscales || a.dL_drotations);
+    if (want_scale_rot) {
+        q_in = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+        sc_in = make_float3(__ldg(a.scales + (size_t)idx * 3), __ldg(a.scales + (size_t)idx * 3 + 1),
+                            __ldg(a.scales + (size_t)idx * 3 + 2));
+    }
+    const unsigned clamp_in = a.shs != nullptr ? (unsigned)geom.clamped[idx] : 0u;
+    V3 sh1 = {0, 0, 0}, sh2 = {0, 0, 0}, sh3 = {0, 0, 0};  // the degree-1 band (the repo's default degree)
+    if (a.shs != nullptr && a.sh_degree > 0) {
+        const float* sp = a.shs + ((size_t)idx * M + 1) * 3;
+        sh1 = V3{__ldg(sp + 0), __ldg(sp + 1), __ldg(sp + 2)};
+        sh2 = V3{__ldg(sp + 3), __ldg(sp + 4), __ldg(sp + 5)};
+        sh3 = V3{__ldg(sp + 6), __ldg(sp + 7), __ldg(sp + 8)};
+    }
+    const float opacity_in = (a.dL_dopacity && (a.grad_mask & GRAD_RAW_PARAMS)) ? geom.splat[idx].q1.w : 0.f;
 
     if (a.dL_dmeans2D) put4<ACC>(a.dL_dmeans2D + (size_t)idx * 4, g_mean2D);
     const bool raw = (a.grad_mask & GRAD_RAW_PARAMS) != 0;  // gradients w.r.t. logits / log-scales / raw quaternions
     if (a.dL_dopacity) {
         float g = g_conic_op.w;
         if (raw) {  // d sigmoid: o (1 - o); the activated opacity is in the saved record (0 for culled Gaussians)
-            const float o = geom.splat[idx].q1.w;
+            const float o = opacity_in;
             g = g * (1.f - o) * o;
         }
         put<ACC>(a.dL_dopacity + idx, g);
@@ -115,9 +144,6 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
     const float* campos = a.vw.campos + (size_t)vi * a.vw.cam_stride;
     const float tan_fovx = a.vw.tanx(vi), tan_fovy = a.vw.tany(vi);
     const float focal_y = a.H / (2.0f * tan_fovy), focal_x = a.W / (2.0f * tan_fovx);
-    const float3 mean = make_float3(a.means3D[(size_t)idx * 3], a.means3D[(size_t)idx * 3 + 1],
-                                    a.means3D[(size_t)idx * 3 + 2]);
-    const float* cov3D = a.cov3D_precomp ? a.cov3D_precomp + (size_t)idx * 6 : geom.cov3D + (size_t)idx * 6;
     float dL_dcov[6];
     float3 dL_dmean;
 
@@ -217,7 +243,7 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
         const float len = sqrtf(dot(dir_orig, dir_orig));
         const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
         const V3* sh = reinterpret_cast<const V3*>(a.shs) + (size_t)idx * M;
-        const unsigned cl = geom.clamped[idx];
+        const unsigned cl = clamp_in;
         V3 dRGB = {g_rgb_depth.x, g_rgb_depth.y, g_rgb_depth.z};
         dRGB.x *= (cl & 1u) ? 0.f : 1.f;
         dRGB.y *= (cl & 2u) ? 0.f : 1.f;
@@ -237,9 +263,9 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
                 putv<ACC>(dsh + 2, (kSH1 * z) * dRGB);
                 putv<ACC>(dsh + 3, (-kSH1 * x) * dRGB);
             }
-            dRGBdx = -kSH1 * sh[3];
-            dRGBdy = -kSH1 * sh[1];
-            dRGBdz = kSH1 * sh[2];
+            dRGBdx = -kSH1 * sh3;
+            dRGBdy = -kSH1 * sh1;
+            dRGBdz = kSH1 * sh2;
             if (deg > 1) {
                 const float xx = x * x, yy = y * y, zz = z * z;
                 const float xy = x * y, yz = y * z, xz = x * z;
@@ -300,9 +326,9 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
         for (int k = 0; k < 6; k++) put<ACC>(a.dL_dcov3D + (size_t)idx * 6 + k, dL_dcov[k]);
 
     // ---- cov3D -> scale, rotation : backward.cu:278-341 ----
-    if (a.scales != nullptr && (a.dL_dscales || a.dL_drotations)) {
-        float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
-        float3 sc = make_float3(a.scales[(size_t)idx * 3], a.scales[(size_t)idx * 3 + 1], a.scales[(size_t)idx * 3 + 2]);
+    if (want_scale_rot) {
+        float4 q = q_in;
+        float3 sc = sc_in;
         float qn = 1.f;
         if (raw) {
             qn = fmaxf(quat_norm(q), 1e-12f);
