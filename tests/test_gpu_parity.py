@@ -206,6 +206,29 @@ def test_long_tile_lists_take_the_merge_path(device):
     assert e_inf <= 2 * GRAD_TOL
 
 
+def test_long_tile_lists_with_exact_depth_ties(device):
+    """Long lists whose depths pile up in a few buckets (a planar sheet facing the camera, every depth repeated
+    many times): the bucket sort must hand over to the bitonic / merge fallback and still give (depth, index) order."""
+    P = 9000
+    sc = SC._scene("long_ties", P, 32, 32, 17, log_scale=math.log(0.01), opacity_mean=-3.0)
+    cam = sc["camera"]
+    Vt = cam["world_view_transform"].double()          # transposed world -> view
+    c2w = torch.linalg.inv(Vt.T)
+    gen = torch.Generator().manual_seed(3)
+    # points on 3 planes of constant view depth, jittered only inside the plane
+    xy = (torch.rand(P, 2, generator=gen, dtype=torch.float64) - 0.5) * 0.05
+    z = torch.tensor([1.7, 1.9, 2.1], dtype=torch.float64)[torch.arange(P) % 3]
+    pv = torch.cat([xy, z[:, None], torch.ones(P, 1, dtype=torch.float64)], 1)
+    sc["means3D"] = (pv @ c2w.T)[:, :3].float().contiguous()
+    st, _ = U.run_oracle(sc)
+    o = U.run_ours(sc, device, tile_cull=False)
+    n_tile = (st.ranges[:, 1].astype(np.int64) - st.ranges[:, 0]).max()
+    assert n_tile > 2048
+    # float32 view depths of one plane are not all bit-identical, but heavily repeated: few distinct keys
+    assert np.array_equal(o["point_list"], st.point_list)
+    assert np.array_equal(o["ranges"], st.ranges)
+
+
 def test_means2d_only_fast_path_matches_full_backward(device):
     """The densify vjp (lightning/network.py:865-872) needs only dL/dmeans2D."""
     from generativedensification_b200 import synthetic as S
