@@ -133,6 +133,8 @@ int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, in
                  int prefiltered, int32_t* radii, void* geom_state, void* image_state, int32_t* num_rendered_host,
                  int flags, cudaStream_t s) {
     if (P < 0 || W <= 0 || H <= 0 || vw.V <= 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
+    if (P >= (1 << gdr::STREAM_REGION_SHIFT))
+        return fail(GDR_ERR_UNSUPPORTED, "%s: at most 2^28 - 1 Gaussians per call", who);
     if (!image_state) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: image_state is NULL", who);
     if (P > 0) {
         if (!g.means3D || !g.opacities || !radii || !geom_state || !vw.view || !vw.proj)

@@ -345,7 +345,7 @@ __device__ __forceinline__ int lower_bound_u64(const uint64_t* a, int n, uint64_
 template <int RQ>
 __global__ void __launch_bounds__(SORT_THREADS)
 tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t* keys0, uint64_t* keys_alt0,
-                 float4* __restrict__ stream0, int64_t capacity, size_t geom_stride, size_t img_stride) {
+                 float4* __restrict__ stream0, int64_t capacity, size_t geom_stride, size_t img_stride, int gx) {
     __shared__ uint64_t s_keys[SORT_CHUNK];
     __shared__ uint32_t s_cnt[BUCKETS];        // bucket histogram, then fill cursors
     __shared__ uint32_t s_start[BUCKETS + 1];  // exclusive scan of the histogram
@@ -589,6 +589,20 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
         float4 w[RQ];
 #pragma unroll
         for (int q = 0; q < RQ; q++) w[q] = __ldg(src4 + q);
+        if constexpr (RQ == 3) {
+            // Which of the tile's four 8x8 regions the splat can reach with alpha >= 1/255 (the exact rectangle
+            // bound the blend kernels would otherwise evaluate once per warp, in the forward AND the backward):
+            // bit 28 + r of the id word.  Gaussian indices stay below 2^28 (checked at the API).
+            const float tx0 = (float)((tile % gx) * TILE), ty0 = (float)((tile / gx) * TILE);
+            unsigned m = 0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const float rx = tx0 + (float)((r & 1) * 8), ry = ty0 + (float)((r >> 1) * 8);
+                if (!splat_misses_rect(w[0].x - rx, w[0].y - ry, w[1].x, w[1].y, w[1].z, w[0].z, 0.f, 0.f, 7.f, 7.f))
+                    m |= 1u << r;
+            }
+            w[0].w = __uint_as_float(__float_as_uint(w[0].w) | (m << STREAM_REGION_SHIFT));
+        }
         float4* dst4 = out + (size_t)i * RQ;
 #pragma unroll
         for (int q = 0; q < RQ; q++) dst4[q] = w[q];
@@ -621,7 +635,7 @@ cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint6
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     tile_sort_kernel<3><<<dim3(gx * gy, max(1, vw.V)), SORT_THREADS, 0, s>>>(
         reinterpret_cast<const float4*>(geom.splat), img, keys, keys_alt, reinterpret_cast<float4*>(stream), capacity,
-        vw.geom_stride, vw.img_stride);
+        vw.geom_stride, vw.img_stride, gx);
     return cudaGetLastError();
 }
 
@@ -630,7 +644,7 @@ cudaError_t launch_tile_sort_surfel(int W, int H, const void* surfel_records, Im
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     tile_sort_kernel<5><<<dim3(gx * gy, 1), SORT_THREADS, 0, s>>>(reinterpret_cast<const float4*>(surfel_records), img,
                                                                   keys, keys_alt, reinterpret_cast<float4*>(surfel_stream),
-                                                                  capacity, 0, 0);
+                                                                  capacity, 0, 0, gx);
     return cudaGetLastError();
 }
 

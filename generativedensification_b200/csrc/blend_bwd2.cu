@@ -159,7 +159,7 @@ __device__ __forceinline__ void flush_batch(WarpScratch& ws, int nb, int lane, f
     const float v1 = -oy * (q1.z * Sy + q1.y * Sx);
     const float v2 = ox * Ax;
     const float v3 = oy * Ay;
-    float* dst = accum + (size_t)__float_as_int(q0.w) * 12;
+    float* dst = accum + (size_t)(__float_as_uint(q0.w) & STREAM_ID_MASK) * 12;
     const bool live = r < nb;
     if constexpr (FULL) {
         float S0 = hsum(S02), Sxx = hsum(Sxx2), Sxy = hsum(Sxy2), Syy = hsum(Syy2);
@@ -345,12 +345,8 @@ blend_backward2_kernel(int P, int W, int H, int gx, ImageState img0, const Splat
         const int ch = n_chunks - 1 - it;
         const int cnt = min(WCHUNK, n - ch * WCHUNK);
         const Splat* sp = &my_buf[it % STAGES][0];
-        bool hit = false;
-        if (lane < cnt) {
-            const float4 q0 = sp[lane].q0;
-            const float4 q1 = sp[lane].q1;
-            hit = !splat_misses_rect(q0.x - region_fx, q0.y - region_fy, q1.x, q1.y, q1.z, q0.z, 0.f, 0.f, 7.f, 7.f);
-        }
+        // lane l reads record l's region bit (tile_sort evaluated the exact rectangle bound for the four regions)
+        const bool hit = lane < cnt && ((__float_as_uint(sp[lane].q0.w) >> (STREAM_REGION_SHIFT + warp)) & 1u);
         unsigned word = __ballot_sync(0xffffffffu, hit);
         // Two visits per round: their exponent / exp / alpha tests are independent and interleave (the kernel is
         // latency-bound at its occupancy); the per-pixel recurrences then run in list order.

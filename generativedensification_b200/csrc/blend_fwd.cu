@@ -18,10 +18,10 @@
 //     reduction and the blend are FFMA2 / FMUL2 / FADD2 (sm_100 packed FP32, the same
 //     IEEE roundings as the scalar code, one issue slot for both pixels), and the
 //     list walk, the shared-memory loads and the votes are paid once per two pixels.
-//     After a chunk lands, the threads classify its records against the four 8x8
-//     regions of the tile with the exact rectangle bound of common.cuh (a 4-bit
-//     mask), and every warp walks only the records whose bit is set for its region
-//     (ballot + find-first-set).  Records that cannot reach alpha = 1/255 anywhere
+//     tile_sort classified every record against the four 8x8 regions of the tile
+//     with the exact rectangle bound of common.cuh (a 4-bit mask in the id word of
+//     the stream copy), and every warp walks only the records whose bit is set for
+//     its region (ballot + find-first-set).  Records that cannot reach alpha = 1/255 anywhere
 //     in a warp's region cost that warp nothing;
 //   * for the pairs that are evaluated, a per-record conservative threshold on the
 //     exponent skips the expf when alpha cannot reach 1/255 (exact: the slack is far
@@ -73,7 +73,6 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
     const bool inside_a = px < W && pya < H, inside_b = px < W && pyb < H;
     const float pxf = (float)px;
     const f32x2 pyf2 = pk((float)pya, (float)pyb);
-    const float region_fx = (float)rx, region_fy = (float)ry;
     uint64_t* my_full = full[warp];
     Splat(*my_buf)[WCHUNK] = buf[warp];
 
@@ -110,13 +109,8 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
         const int cnt = min(WCHUNK, n - c * WCHUNK);
         const Splat* sp = &my_buf[c % STAGES][0];
 
-        // classify: lane l tests record l of the chunk against this warp's 8x8 region (exact rectangle bound)
-        bool hit = false;
-        if (lane < cnt) {
-            const float4 q0 = sp[lane].q0;
-            const float4 q1 = sp[lane].q1;
-            hit = !splat_misses_rect(q0.x - region_fx, q0.y - region_fy, q1.x, q1.y, q1.z, q0.z, 0.f, 0.f, 7.f, 7.f);
-        }
+        // lane l reads record l's region bit (tile_sort evaluated the exact rectangle bound for the four regions)
+        const bool hit = lane < cnt && ((__float_as_uint(sp[lane].q0.w) >> (STREAM_REGION_SHIFT + warp)) & 1u);
         unsigned word = __ballot_sync(0xffffffffu, hit);
         while (word) {
             const int j = __ffs(word) - 1;

@@ -36,7 +36,7 @@ __global__ void unpack_geom_kernel(int P, GeomState g, float* means2D, float* de
 
 __global__ void unpack_list_kernel(int64_t n, const Splat* stream, uint32_t* point_list) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) point_list[i] = __float_as_uint(stream[i].q0.w);
+    if (i < n) point_list[i] = __float_as_uint(stream[i].q0.w) & STREAM_ID_MASK;
 }
 
 __global__ void unpack_ranges_kernel(int T, int64_t capacity, const uint32_t* tile_offsets, uint32_t* ranges) {
