@@ -127,6 +127,19 @@ def test_library_exports_every_declared_symbol():
     assert raw.gdr_geom_state_bytes(ctypes.c_int(-1), ctypes.byref(out)) < 0
     raw.gdr_last_error.restype = ctypes.c_char_p
     assert b"gdr_geom_state_bytes" in raw.gdr_last_error()
+    # argument validation happens on the host, before any CUDA call: bad sizes, the 2^28 Gaussian limit (the id word
+    # of a stream record carries a 4-bit region mask), missing buffers
+    assert _lib.query_bytes("gdr_surfel_state_bytes", 10) >= 800
+    assert _lib.query_bytes("gdr_surfel_aux_bytes", 8, 8) >= 12 * 64
+    nul = ctypes.c_void_p(None)
+    project_args = lambda P, img: (P, 1, 4, 64, 64, nul, nul, nul, nul, nul, 1.0, nul, nul, nul, nul, nul, 1.0, 1.0, 0,
+                                   nul, nul, img, nul, 0, nul)
+    assert lib.gdr_forward_project(*project_args(-1, nul)) == -1
+    assert lib.gdr_forward_project(*project_args(1 << 28, nul)) == -3
+    assert b"2^28" in lib.gdr_last_error()
+    assert lib.gdr_forward_project(*project_args(10, nul)) == -1 and b"image_state" in lib.gdr_last_error()
+    assert lib.gdr_surfel_backward(10, 1, 4, 64, 64, *([nul] * 3), nul, nul, 3, 1.0, *([nul] * 10), 0, *([nul] * 5), 5,
+                                   *([nul] * 9)) == -1
 
 
 def test_library_has_sm100a_code_and_tma_instructions():
@@ -146,6 +159,8 @@ def test_library_has_sm100a_code_and_tma_instructions():
     assert "SYNCS" in sass        # mbarrier
     assert "MATCH" in sass        # warp-aggregated bin counters
     assert "SHFL" in sass and "RED" in sass
+    assert "FFMA2" in sass        # packed FP32 pairs in the blend kernels
+    assert "UCGABAR" in sass      # thread-block cluster barrier (tile_scan's 8-CTA cluster)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/lightning"), reason="reference tree not present")
