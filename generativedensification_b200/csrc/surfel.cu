@@ -99,18 +99,8 @@ __device__ __forceinline__ float surfel_reach(const float Tu[3], const float Tv[
 // Bounding box of the 3-sigma ellipse of the homography T (rows Tu, Tv, Tw).
 __device__ __forceinline__ bool surfel_aabb(const float Tu[3], const float Tv[3], const float Tw[3], float2& centre,
                                             float2& extent) {
-    const float t[3] = {SURFEL_CUTOFF * SURFEL_CUTOFF, SURFEL_CUTOFF * SURFEL_CUTOFF, -1.0f};
-    const float dist = t[0] * Tw[0] * Tw[0] + t[1] * Tw[1] * Tw[1] + t[2] * Tw[2] * Tw[2];
-    if (dist == 0.0f) return false;
-    const float inv = 1.0f / dist;
-    const float f[3] = {t[0] * inv, t[1] * inv, t[2] * inv};
-    centre.x = f[0] * Tu[0] * Tw[0] + f[1] * Tu[1] * Tw[1] + f[2] * Tu[2] * Tw[2];
-    centre.y = f[0] * Tv[0] * Tw[0] + f[1] * Tv[1] * Tw[1] + f[2] * Tv[2] * Tw[2];
-    const float tx = f[0] * Tu[0] * Tu[0] + f[1] * Tu[1] * Tu[1] + f[2] * Tu[2] * Tu[2];
-    const float ty = f[0] * Tv[0] * Tv[0] + f[1] * Tv[1] * Tv[1] + f[2] * Tv[2] * Tv[2];
-    extent.x = sqrtf(fmaxf(1e-4f, centre.x * centre.x - tx));
-    extent.y = sqrtf(fmaxf(1e-4f, centre.y * centre.y - ty));
-    return true;
+    float dist;
+    return surfel_aabb_at(Tu, Tv, Tw, SURFEL_CUTOFF * SURFEL_CUTOFF, centre, extent, dist);
 }
 
 __global__ void __launch_bounds__(SP_THREADS) surfel_project_kernel(const SurfelProjectArgs a) {
