@@ -11,6 +11,9 @@ third_party/diff-gaussian-rasterization).  Layout:
     synthetic.py     seeded synthetic Gaussians + the reference's orbit cameras
     shard.py         view/object sharding over ranks (one process per GPU)
     densify.py       the densify select (vjp of the image loss -> top-K) either side of the path
+    views.py         opt-in batched multi-view entry point (CameraBatch, MultiViewRasterizer, render_images)
+    surfel.py        the diff_surfel_rasterization-shaped 2D-surfel module (+ simple_knn's distCUDA2)
+    coarse_head.py   plain-torch restatement of the coarse Gaussian head that feeds the path (BASELINE configs[0])
 """
 from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians)  # noqa: F401
 
