@@ -121,7 +121,19 @@ def check(status: int, what: str) -> None:
         raise GdrError(f"{what} failed ({status}): {msg.decode() if msg else ''}")
 
 
+_query_cache = {}
+
+
 def query_bytes(fn_name: str, *args) -> int:
-    out = C.c_int64(0)
-    check(getattr(load(), fn_name)(*args, C.byref(out)), fn_name)
-    return int(out.value)
+    """Size of a caller-owned buffer (pure host functions of their arguments: memoised, the drop-in path asks for
+    the same five sizes on every call)."""
+    key = (fn_name, args)
+    v = _query_cache.get(key)
+    if v is None:
+        out = C.c_int64(0)
+        check(getattr(load(), fn_name)(*args, C.byref(out)), fn_name)
+        v = int(out.value)
+        if len(_query_cache) > 4096:
+            _query_cache.clear()
+        _query_cache[key] = v
+    return v
