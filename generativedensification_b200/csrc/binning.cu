@@ -256,7 +256,7 @@ emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii0, GeomState
         // with the culling test repeated exactly as the projection kernel counted it.
         if (__any_sync(0xffffffffu, n > 0)) {
             const int lane = (int)lane_id();
-            warp_foreach_tile(n, x0, y0, w, gx, [&](int tile, int owner, int, bool valid, unsigned) {
+            warp_foreach_tile(n, x0, y0, w, gx, [&](int tile, int owner, int, bool valid, unsigned, int tx, int ty) {
                 const uint32_t o_depth = __shfl_sync(0xffffffffu, depth_bits, owner);
                 const int o_idx = __shfl_sync(0xffffffffu, idx, owner);
                 bool keep = valid;
@@ -265,7 +265,7 @@ emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii0, GeomState
                     const float thr = __shfl_sync(0xffffffffu, q0.z, owner);
                     const float A = __shfl_sync(0xffffffffu, q1.x, owner), B = __shfl_sync(0xffffffffu, q1.y, owner);
                     const float C = __shfl_sync(0xffffffffu, q1.z, owner);
-                    const float tx0 = (float)((tile % gx) * TILE), ty0 = (float)((tile / gx) * TILE);
+                    const float tx0 = (float)(tx * TILE), ty0 = (float)(ty * TILE);
                     keep = valid && !splat_misses_rect(cx, cy, A, B, C, thr, tx0, ty0, tx0 + (TILE - 1), ty0 + (TILE - 1));
                 }
                 const unsigned active = __ballot_sync(0xffffffffu, keep);
@@ -595,10 +595,12 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
             // bit 28 + r of the id word.  Gaussian indices stay below 2^28 (checked at the API).
             const float tx0 = (float)((tile % gx) * TILE), ty0 = (float)((tile / gx) * TILE);
             unsigned m = 0;
+            const float inv_c = __fdiv_rn(-w[1].y, w[1].z), inv_a = __fdiv_rn(-w[1].y, w[1].x);
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const float rx = tx0 + (float)((r & 1) * 8), ry = ty0 + (float)((r >> 1) * 8);
-                if (!splat_misses_rect(w[0].x - rx, w[0].y - ry, w[1].x, w[1].y, w[1].z, w[0].z, 0.f, 0.f, 7.f, 7.f))
+                if (!splat_misses_rect_pre(w[0].x - rx, w[0].y - ry, w[1].x, w[1].y, w[1].z, w[0].z, inv_c, inv_a, 0.f,
+                                           0.f, 7.f, 7.f))
                     m |= 1u << r;
             }
             w[0].w = __uint_as_float(__float_as_uint(w[0].w) | (m << STREAM_REGION_SHIFT));

@@ -283,15 +283,20 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
     const int warp_first_idx = first + (int)(threadIdx.x & ~31u);
     const bool cull = a.cull != 0;
     const int gx = a.gx;
-    warp_foreach_tile(n_tiles, rx0, ry0, rw, gx, [&](int tile, int owner, int local, bool valid, unsigned) {
+    // per-splat constants of the rectangle bound, computed once by the owner lane (the same IEEE divisions the
+    // plain splat_misses_rect performs per call, so emit's cooperative replay takes identical decisions)
+    const float my_inv_c = __fdiv_rn(-rec.q1.y, rec.q1.z), my_inv_a = __fdiv_rn(-rec.q1.y, rec.q1.x);
+    warp_foreach_tile(n_tiles, rx0, ry0, rw, gx, [&](int tile, int owner, int local, bool valid, unsigned, int tx, int ty) {
         bool keep = valid;
         if (cull) {
             const float cx = __shfl_sync(0xffffffffu, rec.q0.x, owner), cy = __shfl_sync(0xffffffffu, rec.q0.y, owner);
             const float thr = __shfl_sync(0xffffffffu, rec.q0.z, owner);
             const float A = __shfl_sync(0xffffffffu, rec.q1.x, owner), B = __shfl_sync(0xffffffffu, rec.q1.y, owner);
             const float C = __shfl_sync(0xffffffffu, rec.q1.z, owner);
-            const float tx0 = (float)((tile % gx) * TILE), ty0 = (float)((tile / gx) * TILE);
-            keep = valid && !splat_misses_rect(cx, cy, A, B, C, thr, tx0, ty0, tx0 + (TILE - 1), ty0 + (TILE - 1));
+            const float inv_c = __shfl_sync(0xffffffffu, my_inv_c, owner), inv_a = __shfl_sync(0xffffffffu, my_inv_a, owner);
+            const float tx0 = (float)(tx * TILE), ty0 = (float)(ty * TILE);
+            keep = valid && !splat_misses_rect_pre(cx, cy, A, B, C, thr, inv_c, inv_a, tx0, ty0, tx0 + (TILE - 1),
+                                                   ty0 + (TILE - 1));
         }
         const unsigned active = __ballot_sync(0xffffffffu, keep);
         if (keep) {

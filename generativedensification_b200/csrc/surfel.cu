@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(SP_THREADS) surfel_project_kernel(const Surfel
         }
         uint32_t* counter = a.img.tile_counter;
         const int warp_first_idx = vb * SP_THREADS + (int)(threadIdx.x & ~31u);
-        warp_foreach_tile(n_tiles, rx0, ry0, rw, a.gx, [&](int tile, int owner, int, bool valid, unsigned) {
+        warp_foreach_tile(n_tiles, rx0, ry0, rw, a.gx, [&](int tile, int owner, int, bool valid, unsigned, int, int) {
             const unsigned active = __ballot_sync(0xffffffffu, valid);
             if (valid) {
                 const int bin = tile * SUBBINS + ((warp_first_idx + owner) & (SUBBINS - 1));

@@ -14,13 +14,16 @@
 
 namespace gdr {
 
-// f(tile_id, owner_lane, local_index, valid, active_mask); invoked by all 32 lanes each step.
+// f(tile_id, owner_lane, local_index, valid, active_mask, tile_x, tile_y); invoked by all 32 lanes each step.
+// local / w is a multiply-high by ceil(2^32 / w), computed once per lane (exact for local, w < 2^16): the
+// per-step integer divisions were a fifth of the walk.
 template <class F>
 __device__ __forceinline__ void warp_foreach_tile(int n, int x0, int y0, int w, int gx, F&& f) {
     const unsigned full = 0xffffffffu;
     const int lane = (int)lane_id();
     const int incl = warp_incl_scan(n);
     const int total = __shfl_sync(full, incl, 31);
+    const unsigned inv_w = w > 1 ? 0xffffffffu / (unsigned)w + 1u : 0u;  // w <= 1: rows are `local` itself
     for (int base = 0; base < total; base += 32) {
         const int j = base + lane;
         int lo = 0, hi = 31;  // smallest lane whose inclusive prefix exceeds j
@@ -35,11 +38,14 @@ __device__ __forceinline__ void warp_foreach_tile(int n, int x0, int y0, int w, 
         const int o_x0 = __shfl_sync(full, x0, owner);
         const int o_y0 = __shfl_sync(full, y0, owner);
         const int o_w = max(1, __shfl_sync(full, w, owner));
+        const unsigned o_inv = __shfl_sync(full, inv_w, owner);
         const bool valid = j < total;
-        const int local = j - o_excl;
-        const int tile = (o_y0 + local / o_w) * gx + o_x0 + local % o_w;
+        const int local = valid ? j - o_excl : 0;
+        const int row = o_w > 1 ? (int)__umulhi((unsigned)local, o_inv) : local;
+        const int tx = o_x0 + (local - row * o_w), ty = o_y0 + row;
+        const int tile = ty * gx + tx;
         const unsigned active = __ballot_sync(full, valid);
-        f(tile, owner, local, valid, active);
+        f(tile, owner, local, valid, active, tx, ty);
     }
 }
 
