@@ -446,6 +446,8 @@ def main():
         step_ms = total_ms / a.steps
         pipe_achieved = (B_f + B_b) * a.views / (step_ms * 1e-3) / 1e9
         pairs_per_view = R * 256.0
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        fp32_peak = torch.cuda.get_device_properties(device).multi_processor_count * 128 * sm_mhz * 1e6
         views_per_s = a.views * a.gpus * a.steps / (total_ms * 1e-3)
         line = dict(base, value=views_per_s, ms_per_step=step_ms,
                     e2e={"value": a.views * a.gpus * a.steps / (e2e_ms * 1e-3), "unit": "views/s",
@@ -461,7 +463,10 @@ def main():
                               "frac_of_hbm_peak": pipe_achieved / hbm_peak, "instances_per_view": R,
                               "instances_per_view_after_culling": R_culled,
                               "pair_evals_per_view": pairs_per_view,
-                              "pair_evals_per_s": pairs_per_view * 2 * views_per_s / a.gpus},
+                              "pair_evals_per_s": pairs_per_view * 2 * views_per_s / a.gpus,
+                              # the blend kernels against the FP32 issue peak (SMs x 128 lanes x clock)
+                              "fp32_lane_ops_peak_per_s": fp32_peak,
+                              "lane_ops_budget_per_pair_eval": fp32_peak / max(pairs_per_view * 2 * views_per_s / a.gpus, 1.0)},
                     batched={"value": a.views * a.gpus * a.steps / (batched_ms * 1e-3), "unit": "views/s",
                              "ms_per_step": batched_ms / a.steps,
                              "e2e_value": a.views * a.gpus * a.steps / (e2e_batched_ms * 1e-3),
