@@ -231,3 +231,29 @@ def test_benchmark_size_surfels_render_and_backpropagate(device):
     for t in grads:
         assert bool(torch.isfinite(t).all())
     assert float(grads[0].abs().max()) > 0
+
+
+def test_capacity_misprediction_and_side_stream(device):
+    """The surfel shim speculates on the instance count like the 3DGS one: a too-small prediction is re-run with the
+    exact capacity, the cold path waits for R, and everything runs on torch's current stream -- same bits each time."""
+    from generativedensification_b200 import surfel as SF
+
+    sc = SCENES["s_deg1_ragged"]
+    gc, ga = SU.surfel_upstream(sc)
+    a = SU.run_ours(sc, device, grads=(gc, ga))
+    P = sc["means3D"].shape[0]
+    key = (device.index, P, sc["camera"]["image_height"], sc["camera"]["image_width"])
+    assert SF._predictor.last[key] > 0
+    SF._predictor.last[key] = 10
+    b = SU.run_ours(sc, device, grads=(gc, ga))
+    SF._predictor.last.pop(key)
+    c = SU.run_ours(sc, device, grads=(gc, ga))
+    s = torch.cuda.Stream(device)
+    with torch.cuda.stream(s):
+        d = SU.run_ours(sc, device, grads=(gc, ga))
+    s.synchronize()
+    for other in (b, c, d):
+        assert torch.equal(a["color"], other["color"]) and torch.equal(a["allmap"], other["allmap"])
+        assert torch.equal(a["radii"], other["radii"])
+        # float atomics: summation order differs from run to run
+        assert SU.rel_err(other["grad_means3D"], a["grad_means3D"]) <= 1e-5
