@@ -59,6 +59,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SCAN_THRE
 tile_scan_kernel(int T, ImageState img0, size_t img_stride) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
+    pdl_wait();  // launched as a programmatic dependent of the projection kernel
     const ImageState img = img0.at(blockIdx.y, img_stride);
     __shared__ ScanShared sh;
     __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
@@ -284,6 +285,7 @@ emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii0, GeomState
         }
     }  // virtual blocks
     if (overflow) atomicOr(&header[HDR_OVERFLOW], 1u);
+    pdl_trigger();  // tile_sort may start launching
 }
 
 constexpr int SORT_THREADS = 256;
@@ -351,6 +353,7 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
     __shared__ uint32_t s_start[BUCKETS + 1];  // exclusive scan of the histogram
     __shared__ uint32_t s_wsum[SORT_THREADS / 32];
     __shared__ uint32_t s_misc[4];             // min depth bits, max depth bits, largest bucket
+    pdl_wait();  // launched as a programmatic dependent of emit
     const int v = blockIdx.y;
     const float4* __restrict__ records =
         reinterpret_cast<const float4*>(reinterpret_cast<const char*>(records0) + (size_t)v * geom_stride);
@@ -609,13 +612,14 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
 #pragma unroll
         for (int q = 0; q < RQ; q++) dst4[q] = w[q];
     }
+    pdl_trigger();  // the forward blend may start launching (empty tiles left above: exiting counts as a trigger)
 }
 
 }  // namespace
 
 cudaError_t launch_tile_scan(int T, ImageState img, const Views& vw, cudaStream_t s) {
-    tile_scan_kernel<<<dim3(SCAN_CLUSTER, max(1, vw.V)), SCAN_THREADS, 0, s>>>(T, img, vw.img_stride);
-    return cudaGetLastError();
+    return launch_dependent(tile_scan_kernel, dim3(SCAN_CLUSTER, max(1, vw.V)), dim3(SCAN_THREADS), 0, s, T, img,
+                            vw.img_stride);
 }
 
 cudaError_t launch_emit(int P, int W, int H, const int32_t* radii, GeomState geom, ImageState img, uint64_t* keys,
@@ -635,10 +639,9 @@ cudaError_t launch_emit(int P, int W, int H, const int32_t* radii, GeomState geo
 cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint64_t* keys, uint64_t* keys_alt,
                              Splat* stream, int64_t capacity, const Views& vw, cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    tile_sort_kernel<3><<<dim3(gx * gy, max(1, vw.V)), SORT_THREADS, 0, s>>>(
-        reinterpret_cast<const float4*>(geom.splat), img, keys, keys_alt, reinterpret_cast<float4*>(stream), capacity,
-        vw.geom_stride, vw.img_stride, gx);
-    return cudaGetLastError();
+    return launch_dependent(tile_sort_kernel<3>, dim3(gx * gy, max(1, vw.V)), dim3(SORT_THREADS), 0, s,
+                            reinterpret_cast<const float4*>(geom.splat), img, keys, keys_alt,
+                            reinterpret_cast<float4*>(stream), capacity, vw.geom_stride, vw.img_stride, gx);
 }
 
 cudaError_t launch_tile_sort_surfel(int W, int H, const void* surfel_records, ImageState img, uint64_t* keys,

@@ -405,6 +405,7 @@ blend_backward2_kernel(int P, int W, int H, int gx, ImageState img0, const Splat
         }
     }
     if (nb > 0) flush_batch<FULL>(ws, nb, lane, region_fx, region_fy, ddelx_dx, ddely_dy, accum);
+    pdl_trigger();  // the per-Gaussian backward may start launching
 }
 
 }  // namespace

@@ -45,6 +45,7 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
     __shared__ __align__(128) Splat buf[WARPS][STAGES][WCHUNK];
     __shared__ __align__(8) uint64_t full[WARPS][STAGES];
 
+    pdl_wait();  // launched as a programmatic dependent of tile_sort
     const int v = blockIdx.y;  // view of the batch
     const ImageState img = img0.at(v, vw.img_stride);
     const uint32_t* __restrict__ tile_offsets = img.tile_offsets;
@@ -206,9 +207,8 @@ cudaError_t launch_blend_forward(int W, int H, ImageState img, const Splat* stre
                                  float* out_color, float* out_depth, float* out_alpha, const Views& vw,
                                  cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    blend_forward_kernel<<<dim3(gx * gy, max(1, vw.V)), BLEND_THREADS, 0, s>>>(W, H, gx, img, stream, capacity, out_color,
-                                                                               out_depth, out_alpha, vw);
-    return cudaGetLastError();
+    return launch_dependent(blend_forward_kernel, dim3(gx * gy, max(1, vw.V)), dim3(BLEND_THREADS), 0, s, W, H, gx, img,
+                            stream, capacity, out_color, out_depth, out_alpha, vw);
 }
 
 }  // namespace gdr

@@ -40,6 +40,7 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
 // stream order after view 0, so the per-Gaussian gradients are summed over views deterministically).
 template <bool ACC>
 __global__ void __launch_bounds__(GB_THREADS) gauss_backward_kernel(const GaussBackwardArgs a) {
+    pdl_wait();  // launched as a programmatic dependent of the backward blend (or of the previous view's launch)
     for (int idx = blockIdx.x * GB_THREADS + threadIdx.x; idx < a.P; idx += gridDim.x * GB_THREADS)
         gauss_backward_one<ACC>(a, idx);
 }
@@ -404,11 +405,8 @@ cudaError_t launch_gauss_backward(const GaussBackwardArgs& a, cudaStream_t s) {
         per_sm < 1)
         per_sm = 1;
     const int grid = min((a.P + GB_THREADS - 1) / GB_THREADS, sm_count() * per_sm);
-    if (a.accumulate)
-        gauss_backward_kernel<true><<<grid, GB_THREADS, 0, s>>>(a);
-    else
-        gauss_backward_kernel<false><<<grid, GB_THREADS, 0, s>>>(a);
-    return cudaGetLastError();
+    return a.accumulate ? launch_dependent(gauss_backward_kernel<true>, dim3(grid), dim3(GB_THREADS), 0, s, a)
+                        : launch_dependent(gauss_backward_kernel<false>, dim3(grid), dim3(GB_THREADS), 0, s, a);
 }
 
 }  // namespace gdr

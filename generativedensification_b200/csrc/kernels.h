@@ -5,7 +5,29 @@
 
 #include "state.cuh"
 
+#include <utility>
+
 namespace gdr {
+
+// Launch `kernel` as a programmatic dependent of the previous kernel in stream `s`: its CTAs may become resident
+// while that kernel's last CTAs are still running and wait in pdl_wait() (common.cuh), so launch latency and CTA
+// ramp-up leave the critical path of the short kernels.  GDR_PDL=0 falls back to plain stream order.
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                             Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // Number of SMs of the current device (cached); grids of the per-Gaussian kernels are sized as a
 // multiple of it and loop over virtual blocks, so no kernel ends with a nearly empty last wave.

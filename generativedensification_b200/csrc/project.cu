@@ -11,6 +11,8 @@
 //   * the same launch bumps the per-tile bin counters with warp-aggregated
 //     atomics (tile_iter.cuh), so no separate counting pass over the Gaussians
 //     and no per-Gaussian prefix sum is needed.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "tile_iter.cuh"
 
@@ -312,6 +314,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
         geom.tile_mask[idx] = (unsigned long long)s_keep[2 * (threadIdx.x & 31)] |
                               ((unsigned long long)s_keep[2 * (threadIdx.x & 31) + 1] << 32);
     }  // virtual blocks
+    pdl_trigger();  // tile_scan may start launching
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
@@ -324,6 +327,14 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 }
 
 }  // namespace
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("GDR_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 
 int sm_count() {
     static int n = 0;
