@@ -161,6 +161,7 @@ def test_library_has_sm100a_code_and_tma_instructions():
     assert "SHFL" in sass and "RED" in sass
     assert "FFMA2" in sass        # packed FP32 pairs in the blend kernels
     assert "UCGABAR" in sass      # thread-block cluster barrier (tile_scan's 8-CTA cluster)
+    assert "ACQBULK" in sass and "PREEXIT" in sass  # programmatic dependent launch (griddepcontrol.wait / .launch_dependents)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/lightning"), reason="reference tree not present")
