@@ -45,7 +45,6 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
     __shared__ __align__(128) Splat buf[WARPS][STAGES][WCHUNK];
     __shared__ __align__(8) uint64_t full[WARPS][STAGES];
 
-    pdl_wait();  // launched as a programmatic dependent of tile_sort
     const int v = blockIdx.y;  // view of the batch
     const ImageState img = img0.at(v, vw.img_stride);
     const uint32_t* __restrict__ tile_offsets = img.tile_offsets;
@@ -83,6 +82,9 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
         mbar_expect_tx(&my_full[c % STAGES], bytes);
         bulk_g2s(&my_buf[c % STAGES][0], src + (size_t)c * WCHUNK, bytes, &my_full[c % STAGES]);
     };
+    // Launched as a programmatic dependent of tile_sort: everything above reads what tile_scan wrote (complete before
+    // emit started); the stream written by tile_sort is first touched below.
+    pdl_wait();
     if (lane == 0) {
 #pragma unroll
         for (int st = 0; st < STAGES; st++) mbar_init(&my_full[st], 1);

@@ -40,7 +40,6 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
 // stream order after view 0, so the per-Gaussian gradients are summed over views deterministically).
 template <bool ACC>
 __global__ void __launch_bounds__(GB_THREADS) gauss_backward_kernel(const GaussBackwardArgs a) {
-    pdl_wait();  // launched as a programmatic dependent of the backward blend (or of the previous view's launch)
     for (int idx = blockIdx.x * GB_THREADS + threadIdx.x; idx < a.P; idx += gridDim.x * GB_THREADS)
         gauss_backward_one<ACC>(a, idx);
 }
@@ -70,16 +69,14 @@ __device__ __forceinline__ void put4(float* p, float4 v) {
 template <bool ACC>
 __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, const int idx) {
     const int vi = a.view;
-    const float4* acc = reinterpret_cast<const float4*>(a.accum + ((size_t)vi * a.P + idx) * 12);
-    const float4 g_mean2D = acc[0];
-    const float4 g_conic_op = acc[1];
-    const float4 g_rgb_depth = acc[2];
     const bool visible = a.radii[(size_t)vi * a.P + idx] > 0;
     const GeomState geom = a.geom.at(vi, a.vw.geom_stride);
     const int M = a.M;
-    // Every per-Gaussian input is fetched here, in ONE round trip with the accumulator loads above: the output
-    // stores below may alias the inputs as far as the compiler knows, so it would issue these loads only after
-    // the stores (which wait for the accumulators) -- two serialized round trips in a latency-bound kernel.
+    // Every per-Gaussian input is fetched here, in ONE round trip: the output stores below may alias the inputs as
+    // far as the compiler knows, so it would issue these loads only after the stores (which wait for the
+    // accumulators) -- two serialized round trips in a latency-bound kernel.  None of them is written by the
+    // backward blend, so as a programmatic dependent of that kernel this launch fetches them while the blend's last
+    // CTAs are still running and only then waits (pdl_wait) for the accumulators.
     const float3 mean = make_float3(__ldg(a.means3D + (size_t)idx * 3), __ldg(a.means3D + (size_t)idx * 3 + 1),
                                     __ldg(a.means3D + (size_t)idx * 3 + 2));
     float cov3D[6];
@@ -106,6 +103,11 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
         sh3 = V3{__ldg(sp + 6), __ldg(sp + 7), __ldg(sp + 8)};
     }
     const float opacity_in = (a.dL_dopacity && (a.grad_mask & GRAD_RAW_PARAMS)) ? geom.splat[idx].q1.w : 0.f;
+    pdl_wait();  // the backward blend (or the previous view's launch of this kernel) has completed
+    const float4* acc = reinterpret_cast<const float4*>(a.accum + ((size_t)vi * a.P + idx) * 12);
+    const float4 g_mean2D = acc[0];
+    const float4 g_conic_op = acc[1];
+    const float4 g_rgb_depth = acc[2];
 
     if (a.dL_dmeans2D) put4<ACC>(a.dL_dmeans2D + (size_t)idx * 4, g_mean2D);
     const bool raw = (a.grad_mask & GRAD_RAW_PARAMS) != 0;  // gradients w.r.t. logits / log-scales / raw quaternions
