@@ -437,8 +437,8 @@ def main():
         dominant = max(stages, key=lambda k: stages[k][0])
         # algorithmic bytes per launch (DESIGN.md "Kernels"): per instance 40 B gather + 4 B id
         alg = {"blend_bwd": 28 * HW + 44 * R + 52 * P, "blend_fwd": 40 * R + 24 * HW,
-               "tile_sort": 8 * R + 48 * R + 48 * R, "emit": 20 * P + 8 * R, "project": P * (44 + 12 * M) + 79 * P,
-               "gauss_bwd": P * (52 + 71 + 12 * M + 64 + 12 * M), "tile_scan": 12 * (HW // 256)}
+               "tile_sort": 8 * R + 48 * R + 48 * R, "project": P * (44 + 12 * M) + 77 * P + 8 * R,
+               "gauss_bwd": P * (52 + 71 + 12 * M + 64 + 12 * M)}
         dom_ms = per_stage[dominant]
         achieved = alg[dominant] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         B_f = P * (48 + 12 * M) + 20 * HW + 68 * R
@@ -453,7 +453,7 @@ def main():
                     e2e={"value": a.views * a.gpus * a.steps / (e2e_ms * 1e-3), "unit": "views/s",
                          "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
                          "ms_per_step": e2e_ms / a.steps},
-                    gpu_launches=7 * a.views * a.steps,
+                    gpu_launches=5 * a.views * a.steps,
                     roofline={"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                               "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": measured_traffic(dominant),
                               "peak_source": f"of {peak_kind}", "ms_per_launch": dom_ms,

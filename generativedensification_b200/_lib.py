@@ -22,6 +22,10 @@ GRAD_MEANS2D, GRAD_MEANS3D, GRAD_COLOR, GRAD_OPACITY, GRAD_COV, GRAD_ALL = 1, 2,
 GRAD_RAW_PARAMS = 32
 FLAG_NO_TILE_CULL = 1
 FLAG_RAW_PARAMS = 2
+FLAG_RERUN = 4
+FLAG_FUSED_EPILOGUE = 8
+COUNT_RENDERED, COUNT_FLAGS, COUNT_MAX_TILE = 0, 1, 2
+COUNT_FLAG_PREFILTERED = 2
 CAMERA_FLOATS = 48
 
 # name -> (restype, argtypes); must list every symbol include/gdr.h declares
@@ -31,16 +35,16 @@ SIGNATURES = {
     "gdr_geom_state_bytes": (_i, [_i, _pi64]),
     "gdr_image_state_bytes": (_i, [_i, _i, _pi64]),
     "gdr_splat_stream_bytes": (_i, [_i64, _pi64]),
-    "gdr_sort_scratch_bytes": (_i, [_i64, _pi64]),
+    "gdr_sort_scratch_bytes": (_i, [_i, _i, _i64, _pi64]),
     "gdr_backward_scratch_bytes": (_i, [_i, _pi64]),
     "gdr_forward_project": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _i,
-                                 _vp, _vp, _vp, _vp, _i, _vp]),
-    "gdr_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
+                                 _vp, _vp, _vp, _vp, _i64, _vp, _i, _vp]),
+    "gdr_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _vp]),
     "gdr_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp,
                           _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gdr_views_forward_project": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _vp, _vp,
-                                       _vp, _vp, _i, _vp]),
-    "gdr_views_forward_render": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
+                                       _vp, _vp, _i64, _vp, _i, _vp]),
+    "gdr_views_forward_render": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _vp]),
     "gdr_views_backward": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
                                 _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gdr_mse_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
@@ -52,8 +56,8 @@ SIGNATURES = {
     "gdr_surfel_aux_bytes": (_i, [_i, _i, _pi64]),
     "gdr_surfel_backward_scratch_bytes": (_i, [_i, _pi64]),
     "gdr_surfel_forward_project": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp,
-                                        _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gdr_surfel_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+                                        _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "gdr_surfel_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _vp]),
     "gdr_surfel_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp]),
@@ -64,7 +68,7 @@ SIGNATURES = {
     "gdr_profile_read": (_i, [C.POINTER(C.c_double), _pi64]),
 }
 
-STAGES = ("project", "tile_scan", "emit", "tile_sort", "blend_fwd", "blend_bwd", "gauss_bwd")
+STAGES = ("project", "tile_sort", "blend_fwd", "blend_bwd", "gauss_bwd")
 
 
 def profile_enable(on: bool) -> None:
@@ -109,8 +113,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.gdr_abi_version() != 1:
-        raise GdrError(f"libgdr.so ABI version {lib.gdr_abi_version()} != 1")
+    if lib.gdr_abi_version() != 2:
+        raise GdrError(f"libgdr.so ABI version {lib.gdr_abi_version()} != 2")
     _lib = lib
     return lib
 

@@ -10,6 +10,8 @@ library has no torch or Python dependency.
 """
 from __future__ import annotations
 
+import contextlib
+import fcntl
 import os
 import subprocess
 import sys
@@ -45,12 +47,31 @@ def is_fresh() -> bool:
     return all(os.path.getmtime(p) <= t for p in _deps() if os.path.exists(p))
 
 
+@contextlib.contextmanager
+def _build_lock():
+    """Exclusive inter-process lock around a build: every rank of a multi-process run may find the library stale at the
+    same time; one of them builds, the others wait here and then find it fresh."""
+    os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, ".lock"), "w") as f:
+        fcntl.flock(f, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(f, fcntl.LOCK_UN)
+
+
 def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
     if not force and is_fresh():
         return LIB
     if not os.path.isfile(NVCC):
         raise RuntimeError(f"nvcc not found at {NVCC}; cannot build libgdr.so")
-    os.makedirs(OBJ, exist_ok=True)
+    with _build_lock():
+        if not force and is_fresh():  # another process built it while we waited for the lock
+            return LIB
+        return _build_locked(verbose, extra_flags)
+
+
+def _build_locked(verbose: bool, extra_flags) -> str:
     srcs = _sources()
 
     def compile_one(src):
@@ -70,10 +91,16 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
         for _, err in results:
             sys.stderr.write(err)
     objs = [o for o, _ in results]
-    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-Xcompiler", "-fPIC"]
+    # objects of sources that no longer exist must not be linked; link into a temporary file and rename it over the
+    # library, so a process that is loading libgdr.so never sees a half-written file
+    tmp = f"{LIB}.tmp.{os.getpid()}"
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs, "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        with contextlib.suppress(OSError):
+            os.unlink(tmp)
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/gdr.h"
@@ -34,7 +35,10 @@ struct StageRecord {
     int stage;
     cudaEvent_t start, stop;
 };
+// The event log is the library's only process-wide state (include/gdr.h says so): the forward and autograd's backward
+// thread both append to it, so it is guarded.
 bool g_profile = false;
+std::mutex g_records_mutex;
 std::vector<StageRecord> g_records;
 
 struct StageTimer {
@@ -51,6 +55,7 @@ struct StageTimer {
     ~StageTimer() {
         if (start) {
             cudaEventRecord(stop, s);
+            std::lock_guard<std::mutex> lock(g_records_mutex);
             g_records.push_back({stage, start, stop});
         }
     }
@@ -84,9 +89,10 @@ int gdr_splat_stream_bytes(int64_t capacity, int64_t* bytes) {
     return GDR_OK;
 }
 
-int gdr_sort_scratch_bytes(int64_t capacity, int64_t* bytes) {
-    if (capacity < 0 || !bytes) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_sort_scratch_bytes: bad arguments");
-    *bytes = 2 * (int64_t)gdr::align_up(sizeof(uint64_t) * (size_t)capacity, 256) + 256;
+int gdr_sort_scratch_bytes(int W, int H, int64_t tile_capacity, int64_t* bytes) {
+    if (W <= 0 || H <= 0 || tile_capacity <= 0 || (tile_capacity & 31) || !bytes)
+        return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_sort_scratch_bytes: bad arguments (tile_capacity must be a positive multiple of 32)");
+    *bytes = (int64_t)gdr::sort_scratch_bytes(W, H, tile_capacity);
     return GDR_OK;
 }
 
@@ -130,8 +136,8 @@ gdr::Views batched_views(int V, int P, int W, int H, const gdr_camera* cams) {
 }
 
 int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, int M, int W, int H, const GaussianInputs& g,
-                 int prefiltered, int32_t* radii, void* geom_state, void* image_state, int32_t* num_rendered_host,
-                 int flags, cudaStream_t s) {
+                 int prefiltered, int32_t* radii, void* geom_state, void* image_state, void* sort_scratch,
+                 int64_t tile_capacity, int32_t* counts_host, int flags, cudaStream_t s) {
     if (P < 0 || W <= 0 || H <= 0 || vw.V <= 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
     if (P >= (1 << gdr::STREAM_REGION_SHIFT))
         return fail(GDR_ERR_UNSUPPORTED, "%s: at most 2^28 - 1 Gaussians per call", who);
@@ -139,6 +145,8 @@ int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, in
     if (P > 0) {
         if (!g.means3D || !g.opacities || !radii || !geom_state || !vw.view || !vw.proj)
             return fail(GDR_ERR_INVALID_ARGUMENT, "%s: a required pointer is NULL", who);
+        if (!sort_scratch || tile_capacity <= 0 || (tile_capacity & 31) || tile_capacity > 0x7fffffff)
+            return fail(GDR_ERR_INVALID_ARGUMENT, "%s: sort_scratch is NULL or tile_capacity is not a positive multiple of 32", who);
         if (!g.shs && !g.colors_precomp)
             return fail(GDR_ERR_INVALID_ARGUMENT, "%s: provide SHs or precomputed colors", who);
         if (!g.colors_precomp && (!vw.campos || M <= 0 || (sh_degree + 1) * (sh_degree + 1) > M || sh_degree < 0 ||
@@ -151,15 +159,13 @@ int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, in
     }
     gdr::ImageState img = gdr::ImageState::carve(image_state, W, H);
     const int T = tiles_of(W, H);
-    const size_t hdr_bytes = sizeof(uint32_t) * gdr::IMG_HEADER_WORDS, cnt_bytes = sizeof(uint32_t) * (size_t)T * gdr::SUBBINS;
-    if (vw.V == 1) {
-        GDR_CUDA(cudaMemsetAsync(img.header, 0, hdr_bytes, s), "memset(header)");
-        GDR_CUDA(cudaMemsetAsync(img.tile_counter, 0, cnt_bytes, s), "memset(tile_counter)");
-    } else {  // one strided memset over the V per-view states
-        GDR_CUDA(cudaMemset2DAsync(img.header, vw.img_stride, 0, hdr_bytes, (size_t)vw.V, s), "memset(header)");
-        GDR_CUDA(cudaMemset2DAsync(img.tile_counter, vw.img_stride, 0, cnt_bytes, (size_t)vw.V, s),
-                 "memset(tile_counter)");
-    }
+    // header and per-tile slot counters are adjacent: one memset (strided over the views of a batch)
+    const size_t zero_bytes = (size_t)((char*)(img.tile_count + T) - (char*)img.header);
+    if (vw.V == 1)
+        GDR_CUDA(cudaMemsetAsync(img.header, 0, zero_bytes, s), "memset(header, tile_count)");
+    else
+        GDR_CUDA(cudaMemset2DAsync(img.header, vw.img_stride, 0, zero_bytes, (size_t)vw.V, s),
+                 "memset(header, tile_count)");
     if (P > 0) {
         gdr::ProjectArgs a;
         a.P = P; a.sh_degree = sh_degree; a.M = M; a.W = W; a.H = H;
@@ -175,55 +181,53 @@ int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, in
         a.radii = radii;
         a.geom = gdr::GeomState::carve(geom_state, (size_t)P);
         a.img = img;
+        a.keys = (uint64_t*)sort_scratch;
+        a.keys_stride = gdr::sort_scratch_bytes(W, H, tile_capacity) / sizeof(uint64_t);
+        a.tile_cap = (uint32_t)tile_capacity;
         {
             StageTimer t(GDR_STAGE_PROJECT, s);
             GDR_CUDA(gdr::launch_project(a, s), "project");
         }
     }
-    {
-        StageTimer t(GDR_STAGE_TILE_SCAN, s);
-        GDR_CUDA(gdr::launch_tile_scan(T, img, vw, s), "tile_scan");
-    }
-    if (num_rendered_host)
-        GDR_CUDA(cudaMemcpy2DAsync(num_rendered_host, sizeof(int32_t), img.header + gdr::HDR_NUM_RENDERED,
-                                   vw.V > 1 ? vw.img_stride : sizeof(int32_t), sizeof(int32_t), (size_t)vw.V,
-                                   cudaMemcpyDeviceToHost, s),
-                 "memcpy(num_rendered)");
+    if (counts_host)  // R, flags, largest tile count, 0 of every view
+        GDR_CUDA(cudaMemcpy2DAsync(counts_host, 4 * sizeof(int32_t), img.header, vw.V > 1 ? vw.img_stride : 4 * sizeof(int32_t),
+                                   4 * sizeof(int32_t), (size_t)vw.V, cudaMemcpyDeviceToHost, s),
+                 "memcpy(counts)");
     return GDR_OK;
 }
 
-int render_impl(const char* who, const gdr::Views& vw, int P, int W, int H, const int32_t* radii, const void* geom_state,
-                void* image_state, void* splat_stream, void* sort_scratch, int64_t capacity, float* out_color,
+int render_impl(const char* who, const gdr::Views& vw, int P, int W, int H, const void* geom_state, void* image_state,
+                void* splat_stream, void* sort_scratch, int64_t tile_capacity, int64_t capacity, float* out_color,
                 float* out_depth, float* out_alpha, int flags, cudaStream_t s) {
     if (P < 0 || W <= 0 || H <= 0 || capacity < 0 || vw.V <= 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
     if (!image_state || !vw.bg || !out_color || !out_depth || !out_alpha)
         return fail(GDR_ERR_INVALID_ARGUMENT, "%s: a required pointer is NULL", who);
-    if (capacity > 0 && (!splat_stream || !sort_scratch))
-        return fail(GDR_ERR_INVALID_ARGUMENT, "%s: stream/scratch is NULL with capacity > 0", who);
-    if (P > 0 && (!geom_state || !radii)) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: geom_state is NULL", who);
+    if (capacity > 0 && !splat_stream) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: stream is NULL with capacity > 0", who);
+    if (P > 0 && (!geom_state || !sort_scratch || tile_capacity <= 0 || (tile_capacity & 31)))
+        return fail(GDR_ERR_INVALID_ARGUMENT, "%s: geom_state / sort_scratch is NULL or bad tile_capacity", who);
+    if (capacity >= ((int64_t)1 << 32)) return fail(GDR_ERR_UNSUPPORTED, "%s: capacity must be below 2^32", who);
     gdr::ImageState img = gdr::ImageState::carve(image_state, W, H);
     gdr::Splat* strm = (gdr::Splat*)splat_stream;
-    if (P > 0 && capacity > 0) {
-        gdr::GeomState geom = gdr::GeomState::carve(const_cast<void*>(geom_state), (size_t)P);
-        const size_t total = (size_t)capacity * (size_t)vw.V;
-        uint64_t* keys = (uint64_t*)sort_scratch;
-        uint64_t* keys_alt = (uint64_t*)((char*)sort_scratch + gdr::align_up(sizeof(uint64_t) * total, 256));
-        // the emit cursors sit at their sub-bin offsets here: tile_scan sets them and tile_sort restores them after use
-        {
-            StageTimer t(GDR_STAGE_EMIT, s);
-            GDR_CUDA(gdr::launch_emit(P, W, H, radii, geom, img, keys, capacity, (flags & GDR_FLAG_NO_TILE_CULL) ? 0 : 1,
-                                      vw, s),
-                     "emit");
-        }
-        {
-            StageTimer t(GDR_STAGE_TILE_SORT, s);
-            GDR_CUDA(gdr::launch_tile_sort(W, H, geom, img, keys, keys_alt, strm, capacity, vw, s), "tile_sort");
-        }
+    if (flags & GDR_FLAG_RERUN) {
+        // a repeated render of the same projection (larger capacity): reset what tile_sort accumulates in the header
+        // -- stream cursor, order-list fills, overflow flag -- but keep what the projection kernel left there
+        const size_t off = sizeof(uint32_t) * gdr::HDR_CURSOR, len = sizeof(uint32_t) * (gdr::IMG_HEADER_WORDS - gdr::HDR_CURSOR);
+        if (vw.V == 1)
+            GDR_CUDA(cudaMemsetAsync((char*)img.header + off, 0, len, s), "memset(header tail)");
+        else
+            GDR_CUDA(cudaMemset2DAsync((char*)img.header + off, vw.img_stride, 0, len, (size_t)vw.V, s), "memset(header tail)");
+    }
+    {
+        gdr::GeomState geom = gdr::GeomState::carve(const_cast<void*>(geom_state), (size_t)(P > 0 ? P : 0));
+        StageTimer t(GDR_STAGE_TILE_SORT, s);
+        // runs for P == 0 too: it files every (empty) tile in the order lists the blend kernel walks
+        GDR_CUDA(gdr::launch_tile_sort(W, H, geom, img, (uint64_t*)sort_scratch, P > 0 ? tile_capacity : 32, strm, capacity, vw,
+                                       s),
+                 "tile_sort");
     }
     {
         StageTimer t(GDR_STAGE_BLEND_FWD, s);
-        GDR_CUDA(gdr::launch_blend_forward(W, H, img, strm, (P > 0) ? capacity : 0, out_color, out_depth, out_alpha, vw,
-                                           s),
+        GDR_CUDA(gdr::launch_blend_forward(W, H, img, strm, capacity, out_color, out_depth, out_alpha, vw, s),
                  "blend_forward");
     }
     return GDR_OK;
@@ -285,19 +289,19 @@ int gdr_forward_project(int P, int sh_degree, int M, int W, int H, const float* 
                         float scale_modifier, const float* rotations, const float* cov3D_precomp,
                         const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
                         float tan_fovy, int prefiltered, int32_t* radii, void* geom_state, void* image_state,
-                        int32_t* num_rendered_host, int flags, void* stream) {
+                        void* sort_scratch, int64_t tile_capacity, int32_t* counts_host, int flags, void* stream) {
     const GaussianInputs g = {means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, scale_modifier};
     return project_impl("gdr_forward_project", single_view(P, W, H, viewmatrix, projmatrix, campos, nullptr, tan_fovx, tan_fovy),
-                        P, sh_degree, M, W, H, g, prefiltered, radii, geom_state, image_state, num_rendered_host, flags,
-                        (cudaStream_t)stream);
+                        P, sh_degree, M, W, H, g, prefiltered, radii, geom_state, image_state, sort_scratch, tile_capacity,
+                        counts_host, flags, (cudaStream_t)stream);
 }
 
-int gdr_forward_render(int P, int W, int H, const float* bg, const int32_t* radii, const void* geom_state,
-                       void* image_state, void* splat_stream, void* sort_scratch, int64_t capacity, float* out_color,
-                       float* out_depth, float* out_alpha, int flags, void* stream) {
-    return render_impl("gdr_forward_render", single_view(P, W, H, nullptr, nullptr, nullptr, bg, 0.f, 0.f), P, W, H, radii,
-                       geom_state, image_state, splat_stream, sort_scratch, capacity, out_color, out_depth, out_alpha,
-                       flags, (cudaStream_t)stream);
+int gdr_forward_render(int P, int W, int H, const float* bg, const void* geom_state, void* image_state,
+                       void* splat_stream, void* sort_scratch, int64_t tile_capacity, int64_t capacity,
+                       float* out_color, float* out_depth, float* out_alpha, int flags, void* stream) {
+    return render_impl("gdr_forward_render", single_view(P, W, H, nullptr, nullptr, nullptr, bg, 0.f, 0.f), P, W, H,
+                       geom_state, image_state, splat_stream, sort_scratch, tile_capacity, capacity, out_color, out_depth,
+                       out_alpha, flags, (cudaStream_t)stream);
 }
 
 int gdr_backward(int P, int sh_degree, int M, int W, int H, const float* bg, const float* means3D, const float* shs,
@@ -322,20 +326,22 @@ int gdr_views_forward_project(int V, int P, int sh_degree, int M, int W, int H, 
                               const float* colors_precomp, const float* opacities, const float* scales,
                               float scale_modifier, const float* rotations, const float* cov3D_precomp,
                               const gdr_camera* cameras, int prefiltered, int32_t* radii, void* geom_states,
-                              void* image_states, int32_t* num_rendered_host, int flags, void* stream) {
+                              void* image_states, void* sort_scratch, int64_t tile_capacity, int32_t* counts_host,
+                              int flags, void* stream) {
     if (V <= 0 || !cameras) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_views_forward_project: bad V or cameras is NULL");
     const GaussianInputs g = {means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, scale_modifier};
     return project_impl("gdr_views_forward_project", batched_views(V, P, W, H, cameras), P, sh_degree, M, W, H, g,
-                        prefiltered, radii, geom_states, image_states, num_rendered_host, flags, (cudaStream_t)stream);
+                        prefiltered, radii, geom_states, image_states, sort_scratch, tile_capacity, counts_host, flags,
+                        (cudaStream_t)stream);
 }
 
-int gdr_views_forward_render(int V, int P, int W, int H, const gdr_camera* cameras, const int32_t* radii,
-                             const void* geom_states, void* image_states, void* splat_streams, void* sort_scratch,
+int gdr_views_forward_render(int V, int P, int W, int H, const gdr_camera* cameras, const void* geom_states,
+                             void* image_states, void* splat_streams, void* sort_scratch, int64_t tile_capacity,
                              int64_t capacity_per_view, float* out_color, float* out_depth, float* out_alpha, int flags,
                              void* stream) {
     if (V <= 0 || !cameras) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_views_forward_render: bad V or cameras is NULL");
-    return render_impl("gdr_views_forward_render", batched_views(V, P, W, H, cameras), P, W, H, radii, geom_states,
-                       image_states, splat_streams, sort_scratch, capacity_per_view, out_color, out_depth, out_alpha,
+    return render_impl("gdr_views_forward_render", batched_views(V, P, W, H, cameras), P, W, H, geom_states, image_states,
+                       splat_streams, sort_scratch, tile_capacity, capacity_per_view, out_color, out_depth, out_alpha,
                        flags, (cudaStream_t)stream);
 }
 
@@ -439,7 +445,8 @@ int gdr_surfel_forward_project(int P, int sh_degree, int M, int W, int H, const 
                                int scale_stride, float scale_modifier, const float* rotations,
                                const float* transmat_precomp, const float* viewmatrix, const float* projmatrix,
                                const float* campos, int32_t* radii, void* geom_state, void* surfel_state,
-                               void* image_state, int32_t* num_rendered_host, void* stream) {
+                               void* image_state, void* sort_scratch, int64_t tile_capacity, int32_t* counts_host,
+                               void* stream) {
     const char* who = "gdr_surfel_forward_project";
     cudaStream_t s = (cudaStream_t)stream;
     if (P < 0 || W <= 0 || H <= 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
@@ -447,6 +454,8 @@ int gdr_surfel_forward_project(int P, int sh_degree, int M, int W, int H, const 
     if (P > 0) {
         if (!means3D || !opacities || !radii || !geom_state || !surfel_state || !viewmatrix || !projmatrix)
             return fail(GDR_ERR_INVALID_ARGUMENT, "%s: a required pointer is NULL", who);
+        if (!sort_scratch || tile_capacity <= 0 || (tile_capacity & 31) || tile_capacity > 0x7fffffff)
+            return fail(GDR_ERR_INVALID_ARGUMENT, "%s: sort_scratch is NULL or tile_capacity is not a positive multiple of 32", who);
         if (!shs && !colors_precomp) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: provide SHs or precomputed colors", who);
         if (!colors_precomp && (!campos || M <= 0 || sh_degree < 0 || sh_degree > 3 || (sh_degree + 1) * (sh_degree + 1) > M))
             return fail(GDR_ERR_INVALID_ARGUMENT, "%s: SH degree / coefficient count mismatch", who);
@@ -457,59 +466,50 @@ int gdr_surfel_forward_project(int P, int sh_degree, int M, int W, int H, const 
     }
     gdr::ImageState img = gdr::ImageState::carve(image_state, W, H);
     const int T = tiles_of(W, H);
-    GDR_CUDA(cudaMemsetAsync(img.header, 0, sizeof(uint32_t) * gdr::IMG_HEADER_WORDS, s), "memset(header)");
-    GDR_CUDA(cudaMemsetAsync(img.tile_counter, 0, sizeof(uint32_t) * (size_t)T * gdr::SUBBINS, s), "memset(tile_counter)");
-    const gdr::Views vw = single_view(P, W, H, viewmatrix, projmatrix, campos, nullptr, 0.f, 0.f);
+    GDR_CUDA(cudaMemsetAsync(img.header, 0, (size_t)((char*)(img.tile_count + T) - (char*)img.header), s),
+             "memset(header, tile_count)");
     if (P > 0) {
         StageTimer t(GDR_STAGE_PROJECT, s);
         GDR_CUDA(gdr::launch_surfel_project(P, sh_degree, M, W, H, means3D, shs, colors_precomp, opacities, scales,
                                             scale_stride, scale_modifier, rotations, transmat_precomp, viewmatrix,
                                             projmatrix, campos, radii, gdr::GeomState::carve(geom_state, (size_t)P),
-                                            surfel_state, img, s),
+                                            surfel_state, img, (uint64_t*)sort_scratch, tile_capacity, s),
                  "surfel_project");
     }
-    {
-        StageTimer t(GDR_STAGE_TILE_SCAN, s);
-        GDR_CUDA(gdr::launch_tile_scan(T, img, vw, s), "tile_scan");
-    }
-    if (num_rendered_host)
-        GDR_CUDA(cudaMemcpyAsync(num_rendered_host, img.header + gdr::HDR_NUM_RENDERED, sizeof(int32_t),
-                                 cudaMemcpyDeviceToHost, s),
-                 "memcpy(num_rendered)");
+    if (counts_host)
+        GDR_CUDA(cudaMemcpyAsync(counts_host, img.header, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s),
+                 "memcpy(counts)");
     return GDR_OK;
 }
 
-int gdr_surfel_forward_render(int P, int W, int H, const float* bg, const int32_t* radii, const void* geom_state,
-                              const void* surfel_state, void* image_state, void* surfel_stream, void* sort_scratch,
-                              int64_t capacity, float* out_color, float* out_allmap, void* surfel_aux, void* stream) {
+int gdr_surfel_forward_render(int P, int W, int H, const float* bg, const void* geom_state, const void* surfel_state,
+                              void* image_state, void* surfel_stream, void* sort_scratch, int64_t tile_capacity,
+                              int64_t capacity, float* out_color, float* out_allmap, void* surfel_aux, int flags,
+                              void* stream) {
     const char* who = "gdr_surfel_forward_render";
     cudaStream_t s = (cudaStream_t)stream;
     if (P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
     if (!image_state || !bg || !out_color || !out_allmap || !surfel_aux)
         return fail(GDR_ERR_INVALID_ARGUMENT, "%s: a required pointer is NULL", who);
-    if (capacity > 0 && (!surfel_stream || !sort_scratch))
-        return fail(GDR_ERR_INVALID_ARGUMENT, "%s: stream/scratch is NULL with capacity > 0", who);
-    if (P > 0 && (!geom_state || !surfel_state || !radii)) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: state is NULL", who);
+    if (capacity > 0 && !surfel_stream) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: stream is NULL with capacity > 0", who);
+    if (P > 0 && (!geom_state || !surfel_state || !sort_scratch || tile_capacity <= 0 || (tile_capacity & 31)))
+        return fail(GDR_ERR_INVALID_ARGUMENT, "%s: state / sort_scratch is NULL or bad tile_capacity", who);
+    if (capacity >= ((int64_t)1 << 32)) return fail(GDR_ERR_UNSUPPORTED, "%s: capacity must be below 2^32", who);
     gdr::ImageState img = gdr::ImageState::carve(image_state, W, H);
-    const gdr::Views vw = single_view(P, W, H, nullptr, nullptr, nullptr, bg, 0.f, 0.f);
-    if (P > 0 && capacity > 0) {
-        gdr::GeomState geom = gdr::GeomState::carve(const_cast<void*>(geom_state), (size_t)P);
-        uint64_t* keys = (uint64_t*)sort_scratch;
-        uint64_t* keys_alt = (uint64_t*)((char*)sort_scratch + gdr::align_up(sizeof(uint64_t) * (size_t)capacity, 256));
-        {
-            StageTimer t(GDR_STAGE_EMIT, s);
-            GDR_CUDA(gdr::launch_emit(P, W, H, radii, geom, img, keys, capacity, /*cull=*/0, vw, s), "emit");
-        }
-        {
-            StageTimer t(GDR_STAGE_TILE_SORT, s);
-            GDR_CUDA(gdr::launch_tile_sort_surfel(W, H, surfel_state, img, keys, keys_alt, surfel_stream, capacity, s),
-                     "tile_sort");
-        }
+    if (flags & GDR_FLAG_RERUN)
+        GDR_CUDA(cudaMemsetAsync(img.header + gdr::HDR_CURSOR, 0,
+                                 sizeof(uint32_t) * (gdr::IMG_HEADER_WORDS - gdr::HDR_CURSOR), s),
+                 "memset(header tail)");
+    {
+        StageTimer t(GDR_STAGE_TILE_SORT, s);
+        GDR_CUDA(gdr::launch_tile_sort_surfel(W, H, surfel_state, img, (uint64_t*)sort_scratch,
+                                              P > 0 ? tile_capacity : 32, surfel_stream, capacity, s),
+                 "tile_sort");
     }
     {
         StageTimer t(GDR_STAGE_BLEND_FWD, s);
-        GDR_CUDA(gdr::launch_surfel_blend_forward(W, H, img, surfel_stream, (P > 0) ? capacity : 0, bg, out_color,
-                                                  out_allmap, (float*)surfel_aux, s),
+        GDR_CUDA(gdr::launch_surfel_blend_forward(W, H, img, surfel_stream, capacity, bg, out_color, out_allmap,
+                                                  (float*)surfel_aux, s),
                  "surfel_blend_forward");
     }
     return GDR_OK;
@@ -595,7 +595,12 @@ int gdr_profile_enable(int on) {
 
 int gdr_profile_read(double* stage_ms, int64_t* stage_launches) {
     if (!stage_ms || !stage_launches) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_profile_read: NULL output");
-    for (auto& r : g_records) {
+    std::vector<StageRecord> records;
+    {
+        std::lock_guard<std::mutex> lock(g_records_mutex);
+        records.swap(g_records);
+    }
+    for (auto& r : records) {
         GDR_CUDA(cudaEventSynchronize(r.stop), "profile sync");
         float ms = 0.f;
         GDR_CUDA(cudaEventElapsedTime(&ms, r.start, r.stop), "profile elapsed");
@@ -606,7 +611,6 @@ int gdr_profile_read(double* stage_ms, int64_t* stage_launches) {
         cudaEventDestroy(r.start);
         cudaEventDestroy(r.stop);
     }
-    g_records.clear();
     return GDR_OK;
 }
 

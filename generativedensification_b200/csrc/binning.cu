@@ -1,292 +1,28 @@
-// Stage 2: tile binning and per-tile depth sort.
+// Stage 2: per-tile depth sort + record gather.
 //
-// Replaces the reference's InclusiveSum + duplicateWithKeys + global 64-bit
-// DeviceRadixSort + identifyTileRanges (RAST/cuda_rasterizer/rasterizer_impl.cu:
-// 278, 70-111, 304-309, 116-138).  The order contract is unchanged: inside a
-// tile, instances are ordered by (view-depth bits ascending, Gaussian index
-// ascending) -- exactly what the reference's stable LSD sort on
+// Replaces the reference's global 64-bit DeviceRadixSort + identifyTileRanges
+// (RAST/cuda_rasterizer/rasterizer_impl.cu:304-309, 116-138).  The order contract is
+// unchanged: inside a tile, instances are ordered by (view-depth bits ascending, Gaussian
+// index ascending) -- exactly what the reference's stable LSD sort on
 // (tile << 32 | depth bits) of idx-major emitted pairs yields.
 //
-// B200-first structure:
-//   tile_scan   a cluster of 8 CTAs scans the per-tile bin counters filled by the
-//               project kernel (partial sums exchanged through distributed shared
-//               memory) -> tile_offsets (the reference's `ranges`), R.
-//   emit        one thread per Gaussian replays the kept-tile bitmask the projection
-//               kernel recorded (rectangles of <= 64 tiles: no culling test, no
-//               cooperation, the slot claims of one thread overlap in flight);
-//               larger rectangles take a warp-cooperative walk over (Gaussian,
-//               tile) pairs with one aggregated atomic per distinct tile.  Writes
-//               the key (depth bits << 32 | idx).  Slot order within a segment is
-//               arbitrary -- the keys are unique, so the sort below makes the
-//               result deterministic.
-//   tile_sort   one CTA per tile sorts its segment in shared memory (bitonic on
-//               u64; segments longer than the smem chunk are chunk-sorted and
-//               merged through global memory) and writes the tile's depth-sorted
-//               48-byte Splat records contiguously, ready for bulk-copy staging
-//               in the blend kernels.
-// Compared with a global 64-bit radix sort of all R pairs (6+ passes over
-// 12 B/pair), each instance is written once as an 8-byte key and read once.
-#include <cooperative_groups.h>
-
+// B200-first structure (the binning itself happens inside the projection kernel, tile_iter.cuh):
+//   tile_sort   one CTA per tile.  Reads the tile's instance count (the projection kernel's
+//               slot counter), allocates the tile's range of the record stream from a global
+//               cursor (tiles lie in completion order; nothing downstream needs tile order),
+//               files the tile in the heaviest-first order lists of the blend kernels, sorts the
+//               tile's key segment in shared memory (monotone depth-bucket sort; a bitonic
+//               network only for short lists and exact depth ties) and writes the tile's
+//               depth-sorted 48-byte Splat records contiguously, ready for bulk-copy staging in
+//               the blend kernels.
+// Compared with a global 64-bit radix sort of all R pairs (6+ passes over 12 B/pair) plus a
+// prefix sum and a duplication pass, each instance is written once as an 8-byte key and read once.
 #include "kernels.h"
 #include "tile_iter.cuh"
 
 namespace gdr {
 
 namespace {
-
-constexpr int SCAN_THREADS = 512;
-constexpr int SCAN_CLUSTER = 8;  // CTAs (SMs) that share one view's scan through distributed shared memory
-
-static_assert(SUBBINS % 4 == 0, "tile_scan_kernel moves a tile's sub-bin counters as 128-bit words");
-constexpr int SUBQ = SUBBINS / 4;  // 128-bit words per tile
-
-struct ScanShared {
-    uint32_t bucket_count[33];  // tiles of this CTA per floor(log2(count)) + 1 bucket; bucket 0 = empty tiles
-    uint32_t bucket_above[33];  // tiles of this CTA in heavier buckets
-    uint32_t total;             // instances in this CTA's tile range
-    uint32_t max_tile;          // largest tile of this CTA's range
-};
-
-// One CLUSTER of SCAN_CLUSTER CTAs per view (a single CTA was bound by one SM's load / store path and by the
-// chain of block-wide barriers: 15 us for 2500 tiles x 8 sub-bins).  CTA r owns the contiguous tile range
-// [r * per_cta, (r + 1) * per_cta): it sums its tiles' sub-bin counters (aligned 128-bit words), publishes its
-// total / largest tile / log2-bucket histogram in its shared memory, and after one cluster barrier every CTA reads
-// its peers' values through DSMEM to get (a) its base offset and (b) where its tiles of each bucket start in the
-// heaviest-first tile order the blend kernels use.  A second cluster barrier keeps every CTA's shared memory alive
-// until all peers have read it.
-__global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SCAN_THREADS)
-tile_scan_kernel(int T, ImageState img0, size_t img_stride) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    pdl_wait();  // launched as a programmatic dependent of the projection kernel
-    const ImageState img = img0.at(blockIdx.y, img_stride);
-    __shared__ ScanShared sh;
-    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
-    __shared__ uint32_t bucket_base[33];
-    __shared__ uint32_t s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int rank = (int)cluster.block_rank();
-    const int per_cta = (T + SCAN_CLUSTER - 1) / SCAN_CLUSTER;
-    const int t0 = min(T, rank * per_cta), t1 = min(T, t0 + per_cta);
-    if (tid < 33) sh.bucket_count[tid] = 0;
-    if (tid == 0) {
-        sh.total = 0;
-        sh.max_tile = 0;
-        s_carry = 0;
-    }
-    __syncthreads();
-    uint4* counters = reinterpret_cast<uint4*>(img.tile_counter);
-    // ---- pass 1: totals, largest tile, bucket histogram of this CTA's range ----
-    uint32_t lmax = 0, lsum = 0;
-    for (int i = t0 + tid; i < t1; i += SCAN_THREADS) {
-        uint32_t c = 0;
-#pragma unroll
-        for (int q = 0; q < SUBQ; q++) {
-            const uint4 a = counters[SUBQ * i + q];
-            c += a.x + a.y + a.z + a.w;
-        }
-        lmax = max(lmax, c);
-        lsum += c;
-        atomicAdd(&sh.bucket_count[c ? 32 - __clz(c) : 0], 1u);
-    }
-    lmax = __reduce_max_sync(0xffffffffu, lmax);
-    lsum = __reduce_add_sync(0xffffffffu, lsum);
-    if (lane == 0) {
-        atomicMax(&sh.max_tile, lmax);
-        atomicAdd(&sh.total, lsum);
-    }
-    __syncthreads();
-    if (wid == 0) {  // lane l owns bucket 32 - l: an inclusive scan from the heaviest bucket down
-        const uint32_t cnt = sh.bucket_count[32 - lane];
-        const uint32_t incl = (uint32_t)warp_incl_scan((int)cnt);
-        sh.bucket_above[32 - lane] = incl - cnt;
-        if (lane == 31) sh.bucket_above[0] = incl;
-    }
-    cluster.sync();  // every CTA's ScanShared is complete and visible cluster-wide
-    // ---- exchange through distributed shared memory ----
-    if (tid < 33) {
-        // heaviest bucket first; inside a bucket the CTAs' tiles follow each other in rank order
-        uint32_t before = 0;
-#pragma unroll
-        for (int r = 0; r < SCAN_CLUSTER; r++) {
-            const ScanShared* peer = cluster.map_shared_rank(&sh, r);
-            before += peer->bucket_above[tid];
-            if (r < rank) before += peer->bucket_count[tid];
-        }
-        bucket_base[tid] = before;
-    }
-    if (tid == 64) {
-        uint32_t base = 0, mx = 0, total = 0;
-#pragma unroll
-        for (int r = 0; r < SCAN_CLUSTER; r++) {
-            const ScanShared* peer = cluster.map_shared_rank(&sh, r);
-            const uint32_t t = peer->total;
-            if (r < rank) base += t;
-            total += t;
-            mx = max(mx, peer->max_tile);
-        }
-        s_carry = base;
-        if (rank == 0) {
-            img.header[HDR_MAX_TILE] = mx;
-            img.header[HDR_NUM_RENDERED] = total;
-            img.tile_offsets[T] = total;
-            img.sub_offsets[T * SUBBINS] = total;
-        }
-    }
-    __syncthreads();
-    // ---- pass 2: chunked block scan of this CTA's range with a running carry ----
-    for (int base = t0; base < t1; base += SCAN_THREADS) {
-        const int i = base + tid;
-        uint4 a[SUBQ];
-        uint32_t c = 0;
-#pragma unroll
-        for (int q = 0; q < SUBQ; q++) {
-            a[q] = i < t1 ? counters[SUBQ * i + q] : make_uint4(0, 0, 0, 0);
-            c += a[q].x + a[q].y + a[q].z + a[q].w;
-        }
-        const int incl = warp_incl_scan((int)c);
-        if (lane == 31) warp_sums[wid] = (uint32_t)incl;
-        __syncthreads();
-        if (wid == 0) {  // exclusive scan of the warp totals
-            const uint32_t ws = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0u;
-            const uint32_t ex = (uint32_t)warp_incl_scan((int)ws) - ws;
-            if (lane < SCAN_THREADS / 32) warp_sums[lane] = ex;
-        }
-        __syncthreads();
-        const uint32_t run = s_carry + warp_sums[wid] + (uint32_t)incl - c;
-        if (i < t1) {
-            img.tile_offsets[i] = run;
-            uint4* so = reinterpret_cast<uint4*>(img.sub_offsets);
-            uint32_t r = run;
-#pragma unroll
-            for (int q = 0; q < SUBQ; q++) {
-                uint4 o;
-                o.x = r;
-                o.y = o.x + a[q].x;
-                o.z = o.y + a[q].y;
-                o.w = o.z + a[q].z;
-                r = o.w + a[q].w;
-                so[SUBQ * i + q] = o;
-                counters[SUBQ * i + q] = o;  // the counters become the emit cursors: they start at the sub-bin's offset
-            }
-            img.tile_order[atomicAdd(&bucket_base[c ? 32 - __clz(c) : 0], 1u)] = (uint32_t)i;
-        }
-        __syncthreads();
-        if (tid == SCAN_THREADS - 1) s_carry = run + c;  // total up to and including this chunk
-        __syncthreads();
-    }
-    cluster.sync();  // no CTA leaves while a peer may still read its shared memory
-}
-
-constexpr int EMIT_THREADS = 128;
-
-// One instance: write the key (depth bits << 32 | Gaussian index) into the claimed slot.  The cursors start at
-// their sub-bin's offset (tile_scan), so a claim IS the position in the key array; the count pass and this pass
-// replay the same kept-tile decisions, so a claim can only leave its segment by exceeding `capacity`.
-__device__ __forceinline__ bool emit_one(uint64_t key, uint64_t* __restrict__ keys, int64_t capacity, uint32_t pos) {
-    if ((int64_t)pos < capacity) {
-        keys[pos] = key;
-        return true;
-    }
-    return false;
-}
-
-__global__ void __launch_bounds__(EMIT_THREADS)
-emit_kernel(int P, int gx, int gy, const int32_t* __restrict__ radii0, GeomState geom0, ImageState img0,
-            uint64_t* __restrict__ keys0, int64_t capacity, int cull, size_t geom_stride, size_t img_stride) {
-    const int v = blockIdx.y;
-    const int32_t* __restrict__ radii = radii0 + (size_t)v * P;
-    const GeomState geom = geom0.at(v, geom_stride);
-    const Splat* __restrict__ splat = geom.splat;
-    const ImageState img = img0.at(v, img_stride);
-    uint32_t* __restrict__ cursor = img.tile_counter;
-    uint32_t* __restrict__ header = img.header;
-    uint64_t* __restrict__ keys = keys0 + (size_t)v * capacity;
-    const int n_vblocks = (P + EMIT_THREADS - 1) / EMIT_THREADS;
-    bool overflow = false;
-    for (int vb = blockIdx.x; vb < n_vblocks; vb += gridDim.x) {  // virtual blocks: balanced single wave
-        const int idx = vb * EMIT_THREADS + threadIdx.x;
-        int n = 0, x0 = 0, y0 = 0, w = 0;
-        uint32_t depth_bits = 0;
-        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
-        unsigned long long m = 0ull;
-        if (idx < P) {
-            // four independent loads (one round trip), then the rectangle
-            const int r = radii[idx];
-            q0 = __ldg(&splat[idx].q0);
-            depth_bits = __float_as_uint(__ldg(&splat[idx].q2.w));
-            m = geom.tile_mask[idx];
-            if (r > 0) {
-                int x1, y1;
-                tile_rect(q0.x, q0.y, r, gx, gy, x0, y0, x1, y1);
-                w = x1 - x0;
-                n = w * (y1 - y0);
-            }
-        }
-        const uint64_t key = ((uint64_t)depth_bits << 32) | (uint32_t)idx;
-        if (n > 0 && n <= 64) {
-            // The common case: replay the kept-tile bitmask the projection kernel recorded for this Gaussian,
-            // one slot claim per kept tile.  Four claims per round with their segment bounds: the atomics and
-            // the loads are all issued before the first result is needed, so their round trips overlap.
-            const uint32_t inv_w = (65536u + (uint32_t)w - 1u) / (uint32_t)w;  // local / w for local < 64, w <= 64
-            while (m) {
-                int bins[4];  // sub-bin ids: tile * SUBBINS + idx % SUBBINS
-                uint32_t base[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    bins[u] = -1;
-                    if (m) {
-                        const int local = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        const int row = (int)(((uint32_t)local * inv_w) >> 16);
-                        bins[u] = ((y0 + row) * gx + x0 + (local - row * w)) * SUBBINS + (idx & (SUBBINS - 1));
-                        base[u] = atomicAdd(&cursor[bins[u]], 1u);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (bins[u] >= 0 && !emit_one(key, keys, capacity, base[u])) overflow = true;
-                }
-            }
-            n = 0;  // done; takes no part in the cooperative walk below
-        } else if (n > 64) {
-            q1 = __ldg(&splat[idx].q1);
-        }
-        // Rectangles of more than 64 tiles (large splats): warp-cooperative walk over the (Gaussian, tile) pairs
-        // with the culling test repeated exactly as the projection kernel counted it.
-        if (__any_sync(0xffffffffu, n > 0)) {
-            const int lane = (int)lane_id();
-            warp_foreach_tile(n, x0, y0, w, gx, [&](int tile, int owner, int, bool valid, unsigned, int tx, int ty) {
-                const uint32_t o_depth = __shfl_sync(0xffffffffu, depth_bits, owner);
-                const int o_idx = __shfl_sync(0xffffffffu, idx, owner);
-                bool keep = valid;
-                if (cull) {  // the identical test project_kernel used when it counted this tile
-                    const float cx = __shfl_sync(0xffffffffu, q0.x, owner), cy = __shfl_sync(0xffffffffu, q0.y, owner);
-                    const float thr = __shfl_sync(0xffffffffu, q0.z, owner);
-                    const float A = __shfl_sync(0xffffffffu, q1.x, owner), B = __shfl_sync(0xffffffffu, q1.y, owner);
-                    const float C = __shfl_sync(0xffffffffu, q1.z, owner);
-                    const float tx0 = (float)(tx * TILE), ty0 = (float)(ty * TILE);
-                    keep = valid && !splat_misses_rect(cx, cy, A, B, C, thr, tx0, ty0, tx0 + (TILE - 1), ty0 + (TILE - 1));
-                }
-                const unsigned active = __ballot_sync(0xffffffffu, keep);
-                if (keep) {
-                    const int bin = tile * SUBBINS + (o_idx & (SUBBINS - 1));
-                    const unsigned peers = __match_any_sync(active, bin);
-                    const int leader = __ffs(peers) - 1;
-                    uint32_t base = 0;
-                    if (lane == leader) base = atomicAdd(&cursor[bin], (unsigned)__popc(peers));
-                    base = __shfl_sync(peers, base, leader);
-                    if (!emit_one(((uint64_t)o_depth << 32) | (uint32_t)o_idx, keys, capacity,
-                                  base + __popc(peers & lanemask_lt())))
-                        overflow = true;
-                }
-            });
-        }
-    }  // virtual blocks
-    if (overflow) atomicOr(&header[HDR_OVERFLOW], 1u);
-    pdl_trigger();  // tile_sort may start launching
-}
 
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_CHUNK = 4096;  // keys per shared-memory sort (32 KB)
@@ -346,32 +82,48 @@ __device__ __forceinline__ int lower_bound_u64(const uint64_t* a, int n, uint64_
 // RQ = 128-bit words per record: 3 for the 48-byte Splat, 5 for the 80-byte Surfel (surfel.cuh).
 template <int RQ>
 __global__ void __launch_bounds__(SORT_THREADS)
-tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t* keys0, uint64_t* keys_alt0,
-                 float4* __restrict__ stream0, int64_t capacity, size_t geom_stride, size_t img_stride, int gx) {
+tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t* keys0, float4* __restrict__ stream0,
+                 int64_t capacity, uint32_t tile_cap, size_t keys_stride, size_t geom_stride, size_t img_stride, int gx,
+                 int T) {
     __shared__ uint64_t s_keys[SORT_CHUNK];
     __shared__ uint32_t s_cnt[BUCKETS];        // bucket histogram, then fill cursors
     __shared__ uint32_t s_start[BUCKETS + 1];  // exclusive scan of the histogram
     __shared__ uint32_t s_wsum[SORT_THREADS / 32];
-    __shared__ uint32_t s_misc[4];             // min depth bits, max depth bits, largest bucket
-    pdl_wait();  // launched as a programmatic dependent of emit
+    __shared__ uint32_t s_misc[4];             // min depth bits, max depth bits, largest bucket, stream base
+    pdl_wait();  // launched as a programmatic dependent of the projection kernel
     const int v = blockIdx.y;
     const float4* __restrict__ records =
         reinterpret_cast<const float4*>(reinterpret_cast<const char*>(records0) + (size_t)v * geom_stride);
     const ImageState img = img0.at(v, img_stride);
-    const uint32_t* __restrict__ tile_offsets = img.tile_offsets;
-    uint32_t* __restrict__ cursor = img.tile_counter;
-    uint64_t* keys = keys0 + (size_t)v * capacity;
-    uint64_t* keys_alt = keys_alt0 + (size_t)v * capacity;
     float4* __restrict__ stream = stream0 + (size_t)v * capacity * RQ;
     const int tile = blockIdx.x;
-    if (threadIdx.x < SUBBINS)  // cursors back at their offsets for a (speculative) re-run
-        cursor[tile * SUBBINS + threadIdx.x] = img.sub_offsets[tile * SUBBINS + threadIdx.x];
-    const int64_t b = min((int64_t)tile_offsets[tile], capacity);
-    const int64_t e = min((int64_t)tile_offsets[tile + 1], capacity);
-    const int n = (int)(e - b);
+    const uint32_t n_binned = min(img.tile_count[tile], tile_cap);  // claims beyond the segment were not stored
+    if (threadIdx.x == 0) {
+        // the tile's range of the stream, and its place in the blend kernels' heaviest-first order
+        uint32_t base = 0, n_fit = 0;
+        if (n_binned) {
+            base = atomicAdd(&img.header[HDR_CURSOR], n_binned);
+            if ((int64_t)base < capacity) n_fit = (uint32_t)min((int64_t)n_binned, capacity - (int64_t)base);
+            else base = 0;
+            if (n_fit < n_binned) atomicOr(&img.header[HDR_SORT_FLAGS], HDR_FLAG_STREAM_OVERFLOW);  // the host re-runs
+        }
+        img.tile_range[tile] = make_uint2(base, base + n_fit);
+        const int bucket = n_fit ? 32 - __clz(n_fit) : 0;
+        img.order[(size_t)bucket * T + atomicAdd(&img.header[HDR_BUCKET0 + bucket], 1u)] = (uint32_t)tile;
+        s_misc[3] = base;
+        s_misc[2] = n_fit;
+    }
+    if (n_binned == 0) return;
+    __syncthreads();
+    const int64_t b = (int64_t)s_misc[3];
+    const int n = (int)s_misc[2];
+    __syncthreads();  // s_misc is reused below
     if (n == 0) return;
-    uint64_t* seg = keys + b;
-    const uint64_t* sorted;  // where the sorted keys end up (shared or global)
+    uint64_t* seg = keys0 + (size_t)v * keys_stride + (size_t)tile * tile_cap;
+    // second key buffer of the long-list paths: the tile's own (not yet written) range of the record stream --
+    // n * RQ * 16 bytes, of which n * 8 are used; the gather below overwrites it after the sorted keys are back in `seg`
+    uint64_t* alt = reinterpret_cast<uint64_t*>(stream + (size_t)b * RQ);
+    const uint64_t* sorted;  // where the sorted keys end up (shared memory or `seg`)
 
     // ---- long lists (dense scenes: 2M Gaussians at 1600^2 give ~5000 instances per covered tile) ----
     // The same monotone depth-bucket sort, with the grouped copy and the result in global memory (both L2-resident
@@ -382,7 +134,7 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
         constexpr int NBIG = 4096;
         uint32_t* big_cnt = reinterpret_cast<uint32_t*>(s_keys);  // [NBIG] histogram, then fill cursors
         uint32_t* big_start = big_cnt + NBIG;                     // [NBIG] exclusive scan
-        uint64_t* grouped = keys_alt + b;
+        uint64_t* grouped = alt;
         uint32_t lo = 0xffffffffu, hi = 0u;
         for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
             const uint32_t d = (uint32_t)(seg[i] >> 32);
@@ -560,7 +312,7 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
         }
         // pairwise merges through global memory (keys are unique, so ranks are unambiguous)
         uint64_t* src = seg;
-        uint64_t* dst = keys_alt + b;
+        uint64_t* dst = alt;
         for (int width = SORT_CHUNK; width < n; width <<= 1) {
             __threadfence_block();
             __syncthreads();
@@ -581,7 +333,12 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
         }
         __threadfence_block();
         __syncthreads();
-        sorted = src;
+        if (src != seg) {  // the gather writes over `alt`: the sorted keys must be in the key segment
+            for (int i = threadIdx.x; i < n; i += SORT_THREADS) seg[i] = src[i];
+            __threadfence_block();
+            __syncthreads();
+        }
+        sorted = seg;
     }
 
     // gather the Gaussians' records into the tile's contiguous, depth-ordered stream
@@ -617,40 +374,22 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
 
 }  // namespace
 
-cudaError_t launch_tile_scan(int T, ImageState img, const Views& vw, cudaStream_t s) {
-    return launch_dependent(tile_scan_kernel, dim3(SCAN_CLUSTER, max(1, vw.V)), dim3(SCAN_THREADS), 0, s, T, img,
-                            vw.img_stride);
-}
-
-cudaError_t launch_emit(int P, int W, int H, const int32_t* radii, GeomState geom, ImageState img, uint64_t* keys,
-                        int64_t capacity, int cull, const Views& vw, cudaStream_t s) {
-    if (P <= 0) return cudaSuccess;
-    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel, EMIT_THREADS, 0) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
-    const int V = max(1, vw.V);
-    const int grid = min((P + EMIT_THREADS - 1) / EMIT_THREADS, max(1, sm_count() * per_sm / V));
-    emit_kernel<<<dim3(grid, V), EMIT_THREADS, 0, s>>>(P, gx, gy, radii, geom, img, keys, capacity, cull, vw.geom_stride,
-                                                       vw.img_stride);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint64_t* keys, uint64_t* keys_alt,
+cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint64_t* keys, int64_t tile_cap,
                              Splat* stream, int64_t capacity, const Views& vw, cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     return launch_dependent(tile_sort_kernel<3>, dim3(gx * gy, max(1, vw.V)), dim3(SORT_THREADS), 0, s,
-                            reinterpret_cast<const float4*>(geom.splat), img, keys, keys_alt,
-                            reinterpret_cast<float4*>(stream), capacity, vw.geom_stride, vw.img_stride, gx);
+                            reinterpret_cast<const float4*>(geom.splat), img, keys, reinterpret_cast<float4*>(stream),
+                            capacity, (uint32_t)tile_cap, sort_scratch_bytes(W, H, tile_cap) / sizeof(uint64_t),
+                            vw.geom_stride, vw.img_stride, gx, gx * gy);
 }
 
 cudaError_t launch_tile_sort_surfel(int W, int H, const void* surfel_records, ImageState img, uint64_t* keys,
-                                    uint64_t* keys_alt, void* surfel_stream, int64_t capacity, cudaStream_t s) {
+                                    int64_t tile_cap, void* surfel_stream, int64_t capacity, cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    tile_sort_kernel<5><<<dim3(gx * gy, 1), SORT_THREADS, 0, s>>>(reinterpret_cast<const float4*>(surfel_records), img,
-                                                                  keys, keys_alt, reinterpret_cast<float4*>(surfel_stream),
-                                                                  capacity, 0, 0, gx);
-    return cudaGetLastError();
+    return launch_dependent(tile_sort_kernel<5>, dim3(gx * gy, 1), dim3(SORT_THREADS), 0, s,
+                            reinterpret_cast<const float4*>(surfel_records), img, keys,
+                            reinterpret_cast<float4*>(surfel_stream), capacity, (uint32_t)tile_cap, (size_t)0, (size_t)0,
+                            (size_t)0, gx, gx * gy);
 }
 
 }  // namespace gdr

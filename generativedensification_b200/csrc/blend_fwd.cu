@@ -5,13 +5,13 @@
 // same exponent expression, full-precision expf, alpha = min(0.99, o*G), skip
 // below 1/255, stop (without blending) when T*(1-alpha) < 1e-4, and
 // out_alpha = sum(alpha*T).  What differs is how the work is organised:
-//   * the tile's depth-sorted Splat records are contiguous (binning.cu), so each
-//     256-record chunk is staged with ONE cp.async.bulk (TMA engine) into a
-//     double-buffered shared-memory ring with mbarrier completion, while the
-//     previous chunk is blended; the reference gathers 28 B per record through
-//     per-thread loads and re-reads colour and depth from global memory for
-//     every contributing (pixel, Gaussian) pair;
-//   * the kernel is instruction-issue bound (ncu: ~90 % issue-slot utilisation), so
+//   * the tile's depth-sorted Splat records are contiguous (binning.cu), so each warp
+//     stages them in 32-record chunks with ONE cp.async.bulk (TMA engine) per chunk into
+//     its own 3-stage shared-memory ring with mbarrier completion -- the four warps of a
+//     CTA never wait for each other; the reference gathers 28 B per record through
+//     per-thread loads and re-reads colour and depth from global memory for every
+//     contributing (pixel, Gaussian) pair;
+//   * the kernel is instruction-issue bound (ncu: 82 % issue-slot utilisation), so
 //     the levers are fewer (pixel, splat) evaluations and fewer issue slots per
 //     evaluation.  A warp owns an 8x8 pixel region, each lane TWO pixels (rows y and
 //     y + 4) whose values travel as packed FP32 pairs: the exponent, the exp range
@@ -28,6 +28,7 @@
 //     larger than any rounding error; everything near the cut takes the reference's
 //     exact test).
 #include "kernels.h"
+#include "tile_iter.cuh"
 
 namespace gdr {
 
@@ -39,7 +40,7 @@ constexpr int WCHUNK = 32;  // records per staged chunk: one record per lane to 
 constexpr int STAGES = 3;   // per-warp ring depth (two chunks in flight behind the one being blended)
 
 __global__ void __launch_bounds__(BLEND_THREADS)
-blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restrict__ stream0, int64_t capacity,
+blend_forward_kernel(int W, int H, int gx, int T, ImageState img0, const Splat* __restrict__ stream0, int64_t capacity,
                      float* __restrict__ out_color0, float* __restrict__ out_depth0, float* __restrict__ out_alpha0,
                      const Views vw) {
     __shared__ __align__(128) Splat buf[WARPS][STAGES][WCHUNK];
@@ -47,8 +48,6 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
 
     const int v = blockIdx.y;  // view of the batch
     const ImageState img = img0.at(v, vw.img_stride);
-    const uint32_t* __restrict__ tile_offsets = img.tile_offsets;
-    const uint32_t* __restrict__ tile_order = img.tile_order;
     uint32_t* __restrict__ n_contrib = img.n_contrib;
     const Splat* __restrict__ stream = stream0 + (size_t)v * capacity;
     const float* __restrict__ bg = vw.bg + (size_t)v * vw.cam_stride;
@@ -56,13 +55,15 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
     float* __restrict__ out_depth = out_depth0 + (size_t)v * H * W;
     float* __restrict__ out_alpha = out_alpha0 + (size_t)v * H * W;
 
-    const int tile = (int)tile_order[blockIdx.x];  // heaviest tiles first
+    // Launched as a programmatic dependent of tile_sort, which wrote everything read from here on (the tile order
+    // lists, the tile ranges, the stream).
+    pdl_wait();
+    const int tile = tile_from_order(img.header, img.order, T, (int)blockIdx.x);  // heaviest tiles first
     const int tile_x = tile % gx, tile_y = tile / gx;
-    const int64_t rb = min((int64_t)tile_offsets[tile], capacity);
-    const int64_t re = min((int64_t)tile_offsets[tile + 1], capacity);
-    const int n = (int)(re - rb);
+    const uint2 range = img.tile_range[tile];
+    const int n = (int)(range.y - range.x);
     const int n_chunks = (n + WCHUNK - 1) / WCHUNK;
-    const Splat* src = stream + rb;
+    const Splat* src = stream + range.x;
 
     // From here on the four warps of the CTA never synchronise with each other: each streams the tile's
     // record list through its own ring and leaves as soon as its own 64 pixels are finished.
@@ -82,9 +83,6 @@ blend_forward_kernel(int W, int H, int gx, ImageState img0, const Splat* __restr
         mbar_expect_tx(&my_full[c % STAGES], bytes);
         bulk_g2s(&my_buf[c % STAGES][0], src + (size_t)c * WCHUNK, bytes, &my_full[c % STAGES]);
     };
-    // Launched as a programmatic dependent of tile_sort: everything above reads what tile_scan wrote (complete before
-    // emit started); the stream written by tile_sort is first touched below.
-    pdl_wait();
     if (lane == 0) {
 #pragma unroll
         for (int st = 0; st < STAGES; st++) mbar_init(&my_full[st], 1);
@@ -209,7 +207,7 @@ cudaError_t launch_blend_forward(int W, int H, ImageState img, const Splat* stre
                                  float* out_color, float* out_depth, float* out_alpha, const Views& vw,
                                  cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    return launch_dependent(blend_forward_kernel, dim3(gx * gy, max(1, vw.V)), dim3(BLEND_THREADS), 0, s, W, H, gx, img,
+    return launch_dependent(blend_forward_kernel, dim3(gx * gy, max(1, vw.V)), dim3(BLEND_THREADS), 0, s, W, H, gx, gx * gy, img,
                             stream, capacity, out_color, out_depth, out_alpha, vw);
 }
 

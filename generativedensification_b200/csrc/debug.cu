@@ -34,19 +34,46 @@ __global__ void unpack_geom_kernel(int P, GeomState g, float* means2D, float* de
     }
 }
 
-__global__ void unpack_list_kernel(int64_t n, const Splat* stream, uint32_t* point_list) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) point_list[i] = __float_as_uint(stream[i].q0.w) & STREAM_ID_MASK;
+// The reference's `ranges` (rasterizer_impl.cu:116-138): tiles in tile order, [begin, end) into its globally sorted
+// point_list; empty tiles stay (0, 0) from its memset (:311).  Our stream keeps the tiles in completion order, so the
+// reference layout is an exclusive scan of the per-tile lengths (one CTA: introspection only).
+__global__ void unpack_ranges_kernel(int T, const uint2* __restrict__ tile_range, uint32_t* __restrict__ ranges) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < T; base += blockDim.x) {
+        const int t = base + threadIdx.x;
+        const uint32_t n = t < T ? tile_range[t].y - tile_range[t].x : 0u;
+        const int incl = warp_incl_scan((int)n);
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = (uint32_t)incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const uint32_t ws = threadIdx.x < (blockDim.x >> 5) ? s_warp[threadIdx.x] : 0u;
+            s_warp[threadIdx.x] = (uint32_t)warp_incl_scan((int)ws) - ws;
+        }
+        __syncthreads();
+        const uint32_t begin = s_carry + s_warp[threadIdx.x >> 5] + (uint32_t)incl - n;
+        if (t < T) {
+            ranges[2 * t] = n ? begin : 0u;
+            ranges[2 * t + 1] = n ? begin + n : 0u;
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = begin + n;
+        __syncthreads();
+    }
 }
 
-__global__ void unpack_ranges_kernel(int T, int64_t capacity, const uint32_t* tile_offsets, uint32_t* ranges) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    const uint32_t b = (uint32_t)min((int64_t)tile_offsets[t], capacity);
-    const uint32_t e = (uint32_t)min((int64_t)tile_offsets[t + 1], capacity);
-    // the reference leaves empty tiles at (0, 0) (memset at rasterizer_impl.cu:311)
-    ranges[2 * t] = e > b ? b : 0;
-    ranges[2 * t + 1] = e > b ? e : 0;
+// point_list in the reference's layout: tile t's sorted ids at ranges[t].
+__global__ void unpack_list_kernel(int64_t capacity, const uint2* __restrict__ tile_range,
+                                   const uint32_t* __restrict__ ranges, const Splat* __restrict__ stream,
+                                   uint32_t* __restrict__ point_list) {
+    const int t = blockIdx.x;
+    const uint2 r = tile_range[t];
+    const uint32_t dst = ranges[2 * t];
+    for (uint32_t i = threadIdx.x; i < r.y - r.x; i += blockDim.x)
+        if ((int64_t)dst + i < capacity)
+            point_list[dst + i] = __float_as_uint(stream[r.x + i].q0.w) & STREAM_ID_MASK;
 }
 
 }  // namespace
@@ -62,9 +89,11 @@ cudaError_t launch_unpack_geom(int P, GeomState geom, float* means2D, float* dep
 cudaError_t launch_unpack_bins(int W, int H, ImageState img, const Splat* stream, int64_t capacity,
                                uint32_t* point_list, uint32_t* ranges, uint32_t* n_contrib, cudaStream_t s) {
     const int T = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
-    if (point_list && capacity > 0)
-        unpack_list_kernel<<<(unsigned)((capacity + 255) / 256), 256, 0, s>>>(capacity, stream, point_list);
-    if (ranges) unpack_ranges_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, capacity, img.tile_offsets, ranges);
+    if (ranges) unpack_ranges_kernel<<<1, 1024, 0, s>>>(T, img.tile_range, ranges);
+    if (point_list && capacity > 0) {
+        if (!ranges) return cudaErrorInvalidValue;
+        unpack_list_kernel<<<T, 128, 0, s>>>(capacity, img.tile_range, ranges, stream, point_list);
+    }
     if (n_contrib) {
         cudaError_t e = cudaMemcpyAsync(n_contrib, img.n_contrib, sizeof(uint32_t) * (size_t)W * H,
                                         cudaMemcpyDeviceToDevice, s);

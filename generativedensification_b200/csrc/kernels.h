@@ -50,6 +50,9 @@ struct ProjectArgs {
     int32_t* radii;    // [V][P]
     GeomState geom;
     ImageState img;
+    uint64_t* keys;      // [V][T][tile_cap] key segments (SortScratch, state.cuh)
+    size_t keys_stride;  // keys between consecutive views
+    uint32_t tile_cap;   // slots per tile segment
 };
 
 // project.cu: per-Gaussian projection + warp-aggregated tile counting
@@ -57,18 +60,15 @@ cudaError_t launch_project(const ProjectArgs& a, cudaStream_t s);
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                                 cudaStream_t s);
 
-// binning.cu: tile scan, instance emission, per-tile depth sort + record gather
-// Batched layout (V = vw.V views, blockIdx.y = view): keys / keys_alt / stream hold `capacity` entries per
-// view back to back; images are [V][C][H][W]; radii [V][P]; accum [V][P][12].
-cudaError_t launch_tile_scan(int T, ImageState img, const Views& vw, cudaStream_t s);
-cudaError_t launch_emit(int P, int W, int H, const int32_t* radii, GeomState geom, ImageState img, uint64_t* keys,
-                        int64_t capacity, int cull, const Views& vw, cudaStream_t s);
-cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint64_t* keys, uint64_t* keys_alt,
+// binning.cu: per-tile depth sort + record gather (the binning itself runs inside the projection kernels)
+// Batched layout (V = vw.V views, blockIdx.y = view): every view has its own key segments (T x tile_cap keys) and
+// `capacity` stream records, back to back; images are [V][C][H][W]; radii [V][P]; accum [V][P][12].
+cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint64_t* keys, int64_t tile_cap,
                              Splat* stream, int64_t capacity, const Views& vw, cudaStream_t s);
 
 // The same per-tile sort with 80-byte Surfel records (surfel.cuh) gathered into the stream; single view.
 cudaError_t launch_tile_sort_surfel(int W, int H, const void* surfel_records, ImageState img, uint64_t* keys,
-                                    uint64_t* keys_alt, void* surfel_stream, int64_t capacity, cudaStream_t s);
+                                    int64_t tile_cap, void* surfel_stream, int64_t capacity, cudaStream_t s);
 
 // blend_fwd.cu
 cudaError_t launch_blend_forward(int W, int H, ImageState img, const Splat* stream, int64_t capacity,
@@ -80,12 +80,6 @@ cudaError_t launch_blend_backward(int P, int W, int H, ImageState img, const Spl
                                   const float* out_alpha, const float* dL_dcolor, const float* dL_ddepth,
                                   const float* dL_dalpha, float* accum, int grad_mask, const Views& vw,
                                   cudaStream_t s);
-
-// blend_bwd2.cu: the same contract, two pixels per lane (the default; launch_blend_backward dispatches to it)
-cudaError_t launch_blend_backward2(int P, int W, int H, ImageState img, const Splat* stream, int64_t capacity,
-                                   const float* out_alpha, const float* dL_dcolor, const float* dL_ddepth,
-                                   const float* dL_dalpha, float* accum, int grad_mask, const Views& vw,
-                                   cudaStream_t s);
 
 struct GaussBackwardArgs {
     int P, sh_degree, M, W, H;
@@ -130,7 +124,7 @@ cudaError_t launch_surfel_project(int P, int sh_degree, int M, int W, int H, con
                                   int scale_stride, float scale_modifier, const float* rotations,
                                   const float* transmat_precomp, const float* view, const float* proj,
                                   const float* campos, int32_t* radii, GeomState geom, void* surfel_state,
-                                  ImageState img, cudaStream_t s);
+                                  ImageState img, uint64_t* keys, int64_t tile_cap, cudaStream_t s);
 cudaError_t launch_surfel_blend_forward(int W, int H, ImageState img, const void* stream, int64_t capacity,
                                         const float* bg, float* out_color, float* out_allmap, float* aux,
                                         cudaStream_t s);

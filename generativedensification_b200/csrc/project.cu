@@ -1,16 +1,19 @@
-// Stage 1: per-Gaussian projection + tile counting (one launch).
+// Stage 1: per-Gaussian projection + tile binning (one launch).
 //
 // Replaces the reference's preprocessCUDA forward
 // (RAST/cuda_rasterizer/forward.cu:155-256 with computeCov3D :118-152,
 // computeCov2D :74-113, computeColorFromSH :20-71, in_frustum auxiliary.h:139-164,
-// getRect auxiliary.h:46-56) and the tiles_touched half of its binning
-// (rasterizer_impl.cu:278 scan input).  Differences in structure, not in values:
+// getRect auxiliary.h:46-56) AND its binning front end: the InclusiveSum over
+// tiles_touched, the blocking read-back of the instance count and
+// duplicateWithKeys (rasterizer_impl.cu:278-301, 70-111).  Differences in
+// structure, not in values:
 //   * inputs with a 12-byte stride (means, scales, SH rows) are staged through
 //     shared memory with coalesced 128-bit loads;
 //   * the outputs of the blend are written as one packed 48-byte Splat record;
-//   * the same launch bumps the per-tile bin counters with warp-aggregated
-//     atomics (tile_iter.cuh), so no separate counting pass over the Gaussians
-//     and no per-Gaussian prefix sum is needed.
+//   * the same launch bins the instances: every (Gaussian, tile) pair that
+//     survives the exact culling test claims a slot of its tile's key segment with
+//     one returning atomic and writes its sort key there (tile_iter.cuh) -- no
+//     count pass, no prefix sum, no second pass over the Gaussians.
 #include <stdlib.h>
 
 #include "kernels.h"
@@ -164,6 +167,14 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
     const GeomState geom = a.geom.at(v, a.vw.geom_stride);
     const ImageState img = a.img.at(v, a.vw.img_stride);
     int32_t* __restrict__ radii = a.radii + (size_t)v * a.P;
+    EmitTarget target;
+    target.tile_count = img.tile_count;
+    target.keys = a.keys + (size_t)v * a.keys_stride;
+    target.tile_cap = a.tile_cap;
+    target.gx = a.gx;
+    __shared__ uint32_t s_tot[2];
+    if (threadIdx.x == 0) s_tot[0] = s_tot[1] = 0u;
+    uint32_t kept = 0, max_fill = 0;
     const int n_vblocks = (a.P + PROJ_THREADS - 1) / PROJ_THREADS;
     for (int vb = blockIdx.x; vb < n_vblocks; vb += gridDim.x) {  // virtual blocks: balanced single wave
     if (vb != (int)blockIdx.x) __syncthreads();                  // the staging buffers are reused
@@ -176,7 +187,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
     float* s_mean = smem;                          // 3 * PROJ_THREADS
     float* s_scale = s_mean + 3 * PROJ_THREADS;    // 3 * PROJ_THREADS
     float* s_sh = s_scale + 3 * PROJ_THREADS;      // 3 * M * PROJ_THREADS
-    const int keep_offset_words = PROJ_THREADS * (6 + 3 * (a.colors_precomp ? 0 : a.M));  // then 2 words per thread
+    const int emit_offset_words = PROJ_THREADS * (6 + 3 * (a.colors_precomp ? 0 : a.M));  // then one EmitRec per thread
     stage_floats(s_mean, a.means3D + (size_t)first * 3, n_items * 3);
     if (a.cov3D_precomp == nullptr) stage_floats(s_scale, a.scales + (size_t)first * 3, n_items * 3);
     const bool use_sh = a.colors_precomp == nullptr;
@@ -201,7 +212,9 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
         const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
         const float3 p_view = xform_point_4x3(p_orig, viewmatrix);
 
-        if (p_view.z > NEAR_Z) {  // near-plane cull only (auxiliary.h:152)
+        // near-plane cull only (auxiliary.h:152: `if (p_view.z <= 0.2f) return false`, so a NaN depth passes, exactly as
+        // in the reference -- such a Gaussian then ends with an empty tile rectangle there and here)
+        if (!(p_view.z <= NEAR_Z)) {
             if (a.cov3D_precomp != nullptr) {
 #pragma unroll
                 for (int k = 0; k < 6; k++) cov3D[k] = __ldg(a.cov3D_precomp + (size_t)idx * 6 + k);
@@ -256,7 +269,8 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
                 }
             }
         } else if (a.prefiltered) {
-            atomicOr(&img.header[HDR_OVERFLOW], 2u);  // reference traps here (auxiliary.h:154-158); we flag
+            atomicOr(&img.header[HDR_PROJECT_FLAGS], HDR_FLAG_PREFILTERED);  // the reference traps here (auxiliary.h:154-158);
+                                                                     // we flag, the host raises
         }
         radii[idx] = radius_out;
         geom.splat[idx] = rec;
@@ -270,51 +284,31 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
         }
     }
 
-    // kept-tile bitmask of each Gaussian (bit = row-major index inside its tile rectangle), gathered from the
-    // pair-parallel walk below through shared-memory atomics; emit_kernel replays it instead of repeating the
-    // culling test.  Only rectangles of <= 64 tiles have one (the others take emit's cooperative path).
-    uint32_t* s_keep = reinterpret_cast<uint32_t*>(smem) + keep_offset_words + 2 * (threadIdx.x & ~31u);
-    s_keep[2 * (threadIdx.x & 31)] = 0u;
-    s_keep[2 * (threadIdx.x & 31) + 1] = 0u;
-    __syncwarp();
-
-    // ---- bin counters: one aggregated atomic per distinct tile per warp step ----
-    // With culling on, a (Gaussian, tile) pair is only counted if the splat can reach alpha >= 1/255
-    // somewhere in the tile (exact: see splat_misses_rect); emit_kernel applies the identical test.
-    uint32_t* counter = img.tile_counter;
-    const int warp_first_idx = first + (int)(threadIdx.x & ~31u);
-    const bool cull = a.cull != 0;
-    const int gx = a.gx;
-    // per-splat constants of the rectangle bound, computed once by the owner lane (the same IEEE divisions the
-    // plain splat_misses_rect performs per call, so emit's cooperative replay takes identical decisions)
-    const float my_inv_c = __fdiv_rn(-rec.q1.y, rec.q1.z), my_inv_a = __fdiv_rn(-rec.q1.y, rec.q1.x);
-    warp_foreach_tile(n_tiles, rx0, ry0, rw, gx, [&](int tile, int owner, int local, bool valid, unsigned, int tx, int ty) {
-        bool keep = valid;
-        if (cull) {
-            const float cx = __shfl_sync(0xffffffffu, rec.q0.x, owner), cy = __shfl_sync(0xffffffffu, rec.q0.y, owner);
-            const float thr = __shfl_sync(0xffffffffu, rec.q0.z, owner);
-            const float A = __shfl_sync(0xffffffffu, rec.q1.x, owner), B = __shfl_sync(0xffffffffu, rec.q1.y, owner);
-            const float C = __shfl_sync(0xffffffffu, rec.q1.z, owner);
-            const float inv_c = __shfl_sync(0xffffffffu, my_inv_c, owner), inv_a = __shfl_sync(0xffffffffu, my_inv_a, owner);
-            const float tx0 = (float)(tx * TILE), ty0 = (float)(ty * TILE);
-            keep = valid && !splat_misses_rect_pre(cx, cy, A, B, C, thr, inv_c, inv_a, tx0, ty0, tx0 + (TILE - 1),
-                                                   ty0 + (TILE - 1));
-        }
-        const unsigned active = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            if (local < 64) atomicOr(&s_keep[2 * owner + (local >> 5)], 1u << (local & 31));
-            // sub-bin = owner's Gaussian index % SUBBINS (the warp's lanes hold consecutive indices)
-            const int bin = tile * SUBBINS + ((warp_first_idx + owner) & (SUBBINS - 1));
-            const unsigned peers = __match_any_sync(active, bin);
-            if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&counter[bin], (unsigned)__popc(peers));
-        }
-    });
-    __syncwarp();
-    if (in_range)
-        geom.tile_mask[idx] = (unsigned long long)s_keep[2 * (threadIdx.x & 31)] |
-                              ((unsigned long long)s_keep[2 * (threadIdx.x & 31) + 1] << 32);
+    // ---- bin the instances: claim a slot of the tile's key segment per kept (Gaussian, tile) pair ----
+    // With culling on, a pair is only binned if the splat can reach alpha >= 1/255 somewhere in the tile
+    // (exact: see splat_misses_rect in common.cuh).
+    EmitRec* s_rec = reinterpret_cast<EmitRec*>(smem + emit_offset_words) + (threadIdx.x & ~31u);
+    const uint32_t depth_bits = __float_as_uint(rec.q2.w);
+    if (a.cull)
+        warp_emit_tiles<true>(s_rec, n_tiles, rx0, ry0, rw, rec.q0, rec.q1, depth_bits, (uint32_t)idx, target, kept,
+                              max_fill);
+    else
+        warp_emit_tiles<false>(s_rec, n_tiles, rx0, ry0, rw, rec.q0, rec.q1, depth_bits, (uint32_t)idx, target, kept,
+                               max_fill);
     }  // virtual blocks
-    pdl_trigger();  // tile_scan may start launching
+    // instance total and largest claim of this CTA: one atomic each per CTA on the view's header
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    max_fill = __reduce_max_sync(0xffffffffu, max_fill);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_tot[0], kept);
+        atomicMax(&s_tot[1], max_fill);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_tot[0]) atomicAdd(&img.header[HDR_NUM_RENDERED], s_tot[0]);
+        if (s_tot[1]) atomicMax(&img.header[HDR_MAX_TILE], s_tot[1]);
+    }
+    pdl_trigger();  // tile_sort may start launching
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
@@ -323,7 +317,7 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
     if (idx >= P) return;
     const float3 p = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
     const float3 v = xform_point_4x3(p, view);
-    present[idx] = v.z > NEAR_Z;
+    present[idx] = !(v.z <= NEAR_Z);  // in_frustum (auxiliary.h:152): NaN passes, as in the reference
 }
 
 }  // namespace
@@ -348,7 +342,8 @@ int sm_count() {
 
 cudaError_t launch_project(const ProjectArgs& a, cudaStream_t s) {
     if (a.P <= 0) return cudaSuccess;
-    const size_t smem = sizeof(float) * PROJ_THREADS * (8 + 3 * (size_t)(a.colors_precomp ? 0 : a.M));
+    const size_t smem = sizeof(float) * PROJ_THREADS * (6 + 3 * (size_t)(a.colors_precomp ? 0 : a.M)) +
+                        sizeof(EmitRec) * PROJ_THREADS;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

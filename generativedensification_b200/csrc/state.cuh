@@ -1,25 +1,26 @@
 // Layout of the caller-owned opaque state buffers (see include/gdr.h).
 //
 // GeomState  (reference: GeometryState, rasterizer_impl.h:33-48) -- per Gaussian:
-//     Splat    splat[P]          48 B   packed blend record (xy, depth, id | conic, opacity | rgb, reject threshold)
+//     Splat    splat[P]          48 B   packed blend record (xy, reject threshold, id | conic, opacity | rgb, depth)
 //     float    cov3D[6P]         24 B   world covariance (needed by the backward)
-//     uint32   tiles_touched[P]   4 B
+//     uint32   tiles_touched[P]   4 B   tiles of the reference's 3-sigma rectangle (before culling)
 //     uint8    clamped[P]         1 B   bit c set <=> SH colour channel c was clamped at 0
-//     uint64   tile_mask[P]       8 B   bit k set <=> tile k (row-major) of the Gaussian's tile rectangle is binned
-//                                       (survived the exact culling test); valid for rectangles of <= 64 tiles
-// ImageState (reference: ImageState, rasterizer_impl.h:50-56) -- per view:
-//     uint32   header[64]               header[0] = R (instances), header[1] = overflow flag
-//     uint32   tile_offsets[T + 1]      exclusive scan of per-tile instance counts (the reference's `ranges`)
-//     uint32   tile_counter[T * SUBBINS] bin counters (count pass, then emit cursors); a tile's segment is the
-//                                       concatenation of SUBBINS sub-segments chosen by (Gaussian index % SUBBINS),
-//                                       so that same-address atomic traffic on the busiest tiles is split SUBBINS ways
-//     uint32   sub_offsets[T * SUBBINS + 1]  exclusive scan of the sub-bin counts (tile_offsets[t] == sub_offsets[t * SUBBINS])
-//     uint32   tile_order[T]            tiles in decreasing-work order (blend kernels: blockIdx -> tile)
+// ImageState (reference: ImageState + the per-tile half of BinningState, rasterizer_impl.h:50-66) -- per view:
+//     uint32   header[64]               see the HDR_* words below
+//     uint32   tile_count[T]            instances binned to each tile: the projection kernel claims a tile's slots with
+//                                       returning atomics on this counter (no count pass, no prefix sum)
+//     uint2    tile_range[T]            [begin, end) of the tile's depth-sorted records in the stream; tile_sort
+//                                       allocates it from a global cursor, so tiles lie in completion order -- nothing
+//                                       downstream needs them in tile order (the reference's `ranges` likewise only
+//                                       holds [begin, end) per tile, rasterizer_impl.cu:116-138)
+//     uint32   order[33][T]             tiles grouped by floor(log2(count)) + 1 (bucket 0 = empty tiles), filled by
+//                                       tile_sort; the blend kernels walk the buckets from the heaviest down
 //     uint32   n_contrib[H * W]
+// SortScratch (temporary): uint64 keys[T][tile_capacity]  -- key = depth bits << 32 | Gaussian index; a tile's
+//                                       segment has a fixed capacity chosen by the host from the previous frame
 // SplatStream (reference: BinningState.point_list, but materialised):
 //     Splat    stream[capacity]         per-tile, depth-sorted copies of the Gaussians' records,
 //                                       contiguous per tile so a tile is staged with cp.async.bulk
-// SortScratch: uint64 keys[capacity], uint64 keys_alt[capacity]
 #pragma once
 #include "common.cuh"
 
@@ -32,14 +33,12 @@ struct GeomState {
     float* cov3D;
     uint32_t* tiles_touched;
     uint8_t* clamped;
-    unsigned long long* tile_mask;
     static __host__ __device__ size_t bytes(size_t P) {
         size_t o = 0;
         o = align_up(o + sizeof(Splat) * P, 256);
         o = align_up(o + sizeof(float) * 6 * P, 256);
         o = align_up(o + sizeof(uint32_t) * P, 256);
         o = align_up(o + P, 256);
-        o = align_up(o + sizeof(unsigned long long) * P, 256);
         return o + 256;
     }
     static __host__ __device__ GeomState carve(void* base, size_t P) {
@@ -53,8 +52,6 @@ struct GeomState {
         g.tiles_touched = (uint32_t*)(p + o);
         o = align_up(o + sizeof(uint32_t) * P, 256);
         g.clamped = (uint8_t*)(p + o);
-        o = align_up(o + P, 256);
-        g.tile_mask = (unsigned long long*)(p + o);
         return g;
     }
     // the same state of view v of a batch whose per-view states are `stride` bytes apart
@@ -65,65 +62,75 @@ struct GeomState {
         g.cov3D = (float*)((char*)cov3D + off);
         g.tiles_touched = (uint32_t*)((char*)tiles_touched + off);
         g.clamped = clamped + off;
-        g.tile_mask = (unsigned long long*)((char*)tile_mask + off);
         return g;
     }
 };
 
 constexpr int IMG_HEADER_WORDS = 64;
-constexpr int SUBBINS = 8;  // sub-counters per tile (see ImageState)
-constexpr int HDR_NUM_RENDERED = 0;
-constexpr int HDR_OVERFLOW = 1;
-constexpr int HDR_MAX_TILE = 2;
+constexpr int ORDER_BUCKETS = 33;   // floor(log2(count)) + 1 for count > 0, bucket 0 = empty tiles
+// header words.  The first four are what the host reads back (gdr_forward_project's counts_host); words from
+// HDR_CURSOR on belong to tile_sort and are reset when a render is repeated with a larger stream capacity.
+constexpr int HDR_NUM_RENDERED = 0;  // R: instances binned (after tile culling), summed by the projection kernel
+constexpr int HDR_PROJECT_FLAGS = 1; // HDR_FLAG_PREFILTERED
+constexpr int HDR_MAX_TILE = 2;      // largest per-tile instance count (may exceed the tile capacity: then re-run)
+constexpr int HDR_CURSOR = 4;        // tile_sort's stream allocation cursor
+constexpr int HDR_SORT_FLAGS = 5;    // HDR_FLAG_STREAM_OVERFLOW
+constexpr int HDR_BUCKET0 = 8;       // ORDER_BUCKETS fill counts of the order lists
+constexpr uint32_t HDR_FLAG_STREAM_OVERFLOW = 1u;  // a tile's records did not fit the stream capacity (tile_sort)
+constexpr uint32_t HDR_FLAG_PREFILTERED = 2u;      // prefiltered = true but a Gaussian failed the near-plane test
+static_assert(HDR_BUCKET0 + ORDER_BUCKETS <= IMG_HEADER_WORDS, "header too small");
 
 struct ImageState {
     uint32_t* header;
-    uint32_t* tile_offsets;
-    uint32_t* tile_counter;
-    uint32_t* tile_order;
+    uint32_t* tile_count;
+    uint2* tile_range;
+    uint32_t* order;
     uint32_t* n_contrib;
-    uint32_t* sub_offsets;
+    static __host__ __device__ size_t tiles(int W, int H) {
+        return (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    }
     static __host__ __device__ size_t bytes(int W, int H) {
-        const size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+        const size_t T = tiles(W, H);
         size_t o = 0;
         o = align_up(o + 4 * IMG_HEADER_WORDS, 256);
-        o = align_up(o + 4 * (T + 1), 256);
-        o = align_up(o + 4 * T * SUBBINS, 256);
         o = align_up(o + 4 * T, 256);
+        o = align_up(o + 8 * T, 256);
+        o = align_up(o + 4 * T * ORDER_BUCKETS, 256);
         o = align_up(o + 4 * (size_t)W * H, 256);
-        o = align_up(o + 4 * (T * SUBBINS + 1), 256);
         return o + 256;
     }
     static __host__ __device__ ImageState carve(void* base, int W, int H) {
-        const size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+        const size_t T = tiles(W, H);
         ImageState s;
         char* p = (char*)base;
         size_t o = 0;
         s.header = (uint32_t*)(p + o);
         o = align_up(o + 4 * IMG_HEADER_WORDS, 256);
-        s.tile_offsets = (uint32_t*)(p + o);
-        o = align_up(o + 4 * (T + 1), 256);
-        s.tile_counter = (uint32_t*)(p + o);
-        o = align_up(o + 4 * T * SUBBINS, 256);
-        s.tile_order = (uint32_t*)(p + o);
+        s.tile_count = (uint32_t*)(p + o);
         o = align_up(o + 4 * T, 256);
+        s.tile_range = (uint2*)(p + o);
+        o = align_up(o + 8 * T, 256);
+        s.order = (uint32_t*)(p + o);
+        o = align_up(o + 4 * T * ORDER_BUCKETS, 256);
         s.n_contrib = (uint32_t*)(p + o);
-        o = align_up(o + 4 * (size_t)W * H, 256);
-        s.sub_offsets = (uint32_t*)(p + o);
         return s;
     }
     __host__ __device__ ImageState at(int v, size_t stride) const {
         ImageState s;
         const size_t off = (size_t)v * stride;
         s.header = (uint32_t*)((char*)header + off);
-        s.tile_offsets = (uint32_t*)((char*)tile_offsets + off);
-        s.tile_counter = (uint32_t*)((char*)tile_counter + off);
-        s.tile_order = (uint32_t*)((char*)tile_order + off);
+        s.tile_count = (uint32_t*)((char*)tile_count + off);
+        s.tile_range = (uint2*)((char*)tile_range + off);
+        s.order = (uint32_t*)((char*)order + off);
         s.n_contrib = (uint32_t*)((char*)n_contrib + off);
-        s.sub_offsets = (uint32_t*)((char*)sub_offsets + off);
         return s;
     }
 };
+
+// Bytes of one view's key segments: T tiles x tile_capacity keys (tile_capacity a multiple of 32).
+__host__ __device__ inline size_t sort_scratch_bytes(int W, int H, int64_t tile_capacity) {
+    return align_up(ImageState::tiles(W, H) * (size_t)tile_capacity * sizeof(uint64_t), 256);
+}
 
 // How a kernel finds view v = blockIdx.y of a batch of V views that share one set of Gaussians.
 // The single-view entry points use V = 1 with every stride 0 and the tangents passed by value; the

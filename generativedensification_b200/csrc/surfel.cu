@@ -57,6 +57,8 @@ struct SurfelProjectArgs {
     GeomState geom;
     Surfel* surfel;
     ImageState img;
+    uint64_t* keys;     // [T][tile_cap] key segments (SortScratch, state.cuh)
+    uint32_t tile_cap;
 };
 
 // Bounding box of the ellipse rho3d <= cutoff^2 of the homography T (rows Tu, Tv, Tw).
@@ -104,12 +106,23 @@ __device__ __forceinline__ bool surfel_aabb(const float Tu[3], const float Tv[3]
 }
 
 __global__ void __launch_bounds__(SP_THREADS) surfel_project_kernel(const SurfelProjectArgs a) {
+    __shared__ EmitRec s_emit[SP_THREADS];
+    __shared__ uint32_t s_tot[2];
     float Q[4][3];
     world_to_pixel_hom(a.proj, a.W, a.H, Q);
+    EmitTarget target;
+    target.tile_count = a.img.tile_count;
+    target.keys = a.keys;
+    target.tile_cap = a.tile_cap;
+    target.gx = a.gx;
+    if (threadIdx.x == 0) s_tot[0] = s_tot[1] = 0u;
+    __syncthreads();
+    uint32_t kept = 0, max_fill = 0;
     const int n_vblocks = (a.P + SP_THREADS - 1) / SP_THREADS;
     for (int vb = blockIdx.x; vb < n_vblocks; vb += gridDim.x) {
         const int idx = vb * SP_THREADS + threadIdx.x;
         int n_tiles = 0, rx0 = 0, ry0 = 0, rw = 0;
+        uint32_t depth_bits = 0;
         if (idx < a.P) {
             int radius_out = 0;
             unsigned clamp_bits = 0;
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(SP_THREADS) surfel_project_kernel(const Surfel
             }
             a.radii[idx] = radius_out;
             a.surfel[idx] = rec;
-            // the shared binning kernels read the centre, the depth and the kept-tile mask from the 3DGS-shaped state
+            // debug introspection reads the centre and the depth from the 3DGS-shaped state
             Splat b;
             b.q0 = make_float4(rec.r0.x, rec.r0.y, 0.f, __int_as_float(idx));
             b.q1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -198,19 +211,25 @@ __global__ void __launch_bounds__(SP_THREADS) surfel_project_kernel(const Surfel
             a.geom.splat[idx] = b;
             a.geom.tiles_touched[idx] = (uint32_t)n_tiles;
             a.geom.clamped[idx] = (uint8_t)clamp_bits;
-            a.geom.tile_mask[idx] = n_tiles >= 64 ? ~0ull : ((1ull << n_tiles) - 1ull);  // no tile-level culling here
+            depth_bits = __float_as_uint(pv.z);
         }
-        uint32_t* counter = a.img.tile_counter;
-        const int warp_first_idx = vb * SP_THREADS + (int)(threadIdx.x & ~31u);
-        warp_foreach_tile(n_tiles, rx0, ry0, rw, a.gx, [&](int tile, int owner, int, bool valid, unsigned, int, int) {
-            const unsigned active = __ballot_sync(0xffffffffu, valid);
-            if (valid) {
-                const int bin = tile * SUBBINS + ((warp_first_idx + owner) & (SUBBINS - 1));
-                const unsigned peers = __match_any_sync(active, bin);
-                if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&counter[bin], (unsigned)__popc(peers));
-            }
-        });
+        // bin the instances (no tile-level culling on this path): one slot claim + key per (surfel, tile) pair
+        const float4 unused = make_float4(0.f, 0.f, 0.f, 0.f);
+        warp_emit_tiles<false>(s_emit + (threadIdx.x & ~31u), n_tiles, rx0, ry0, rw, unused, unused, depth_bits,
+                               (uint32_t)idx, target, kept, max_fill);
     }
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    max_fill = __reduce_max_sync(0xffffffffu, max_fill);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_tot[0], kept);
+        atomicMax(&s_tot[1], max_fill);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_tot[0]) atomicAdd(&a.img.header[HDR_NUM_RENDERED], s_tot[0]);
+        if (s_tot[1]) atomicMax(&a.img.header[HDR_MAX_TILE], s_tot[1]);
+    }
+    pdl_trigger();  // tile_sort may start launching
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -275,16 +294,17 @@ __device__ __forceinline__ void classify_chunk(const Surfel* sp, int cnt, int la
 }
 
 __global__ void __launch_bounds__(SB_THREADS)
-surfel_blend_forward_kernel(int W, int H, int gx, ImageState img, const Surfel* __restrict__ stream, int64_t capacity,
+surfel_blend_forward_kernel(int W, int H, int gx, int n_tiles_total, ImageState img, const Surfel* __restrict__ stream, int64_t capacity,
                             const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_allmap,
                             float* __restrict__ aux) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SurfelSmem& sm = *reinterpret_cast<SurfelSmem*>(smem_raw);
-    const int tile = (int)img.tile_order[blockIdx.x];
+    pdl_wait();  // launched as a programmatic dependent of tile_sort
+    const int tile = tile_from_order(img.header, img.order, n_tiles_total, (int)blockIdx.x);
     const int tile_x = tile % gx, tile_y = tile / gx;
-    const int64_t rb = min((int64_t)img.tile_offsets[tile], capacity);
-    const int64_t re = min((int64_t)img.tile_offsets[tile + 1], capacity);
-    const int n = (int)(re - rb);
+    const uint2 range = img.tile_range[tile];
+    const int64_t rb = (int64_t)range.x;
+    const int n = (int)(range.y - range.x);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = tile_x * TILE + (warp & 1) * 8 + (lane & 7);
     const int py = tile_y * TILE + (warp >> 1) * 4 + (lane >> 3);
@@ -403,17 +423,17 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
 }
 
 __global__ void __launch_bounds__(SB_THREADS)
-surfel_blend_backward_kernel(int W, int H, int gx, ImageState img, const Surfel* __restrict__ stream, int64_t capacity,
+surfel_blend_backward_kernel(int W, int H, int gx, int n_tiles_total, ImageState img, const Surfel* __restrict__ stream, int64_t capacity,
                              const float* __restrict__ bg, const float* __restrict__ out_allmap,
                              const float* __restrict__ aux, const float* __restrict__ dL_dcolor,
                              const float* __restrict__ dL_dallmap, float* __restrict__ accum) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SurfelSmem& sm = *reinterpret_cast<SurfelSmem*>(smem_raw);
-    const int tile = (int)img.tile_order[blockIdx.x];
+    const int tile = tile_from_order(img.header, img.order, n_tiles_total, (int)blockIdx.x);
     const int tile_x = tile % gx, tile_y = tile / gx;
-    const int64_t rb = min((int64_t)img.tile_offsets[tile], capacity);
-    const int64_t re = min((int64_t)img.tile_offsets[tile + 1], capacity);
-    const int n_all = (int)(re - rb);
+    const uint2 range = img.tile_range[tile];
+    const int64_t rb = (int64_t)range.x;
+    const int n_all = (int)(range.y - range.x);
     if (n_all == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = tile_x * TILE + (warp & 1) * 8 + (lane & 7);
@@ -725,7 +745,7 @@ cudaError_t launch_surfel_project(int P, int sh_degree, int M, int W, int H, con
                                   int scale_stride, float scale_modifier, const float* rotations,
                                   const float* transmat_precomp, const float* view, const float* proj,
                                   const float* campos, int32_t* radii, GeomState geom, void* surfel_state,
-                                  ImageState img, cudaStream_t s) {
+                                  ImageState img, uint64_t* keys, int64_t tile_cap, cudaStream_t s) {
     if (P <= 0) return cudaSuccess;
     SurfelProjectArgs a;
     a.P = P; a.sh_degree = sh_degree; a.M = M; a.W = W; a.H = H;
@@ -734,6 +754,7 @@ cudaError_t launch_surfel_project(int P, int sh_degree, int M, int W, int H, con
     a.scale_stride = scale_stride; a.scale_modifier = scale_modifier; a.rotations = rotations;
     a.transmat_precomp = transmat_precomp; a.view = view; a.proj = proj; a.campos = campos;
     a.radii = radii; a.geom = geom; a.surfel = (Surfel*)surfel_state; a.img = img;
+    a.keys = keys; a.tile_cap = (uint32_t)tile_cap;
     const int n_vblocks = (P + SP_THREADS - 1) / SP_THREADS;
     const int grid = min(n_vblocks, sm_count() * 8);
     surfel_project_kernel<<<grid, SP_THREADS, 0, s>>>(a);
@@ -748,7 +769,7 @@ cudaError_t launch_surfel_blend_forward(int W, int H, ImageState img, const void
                                          (int)sizeof(SurfelSmem));
     if (e != cudaSuccess) return e;
     surfel_blend_forward_kernel<<<gx * gy, SB_THREADS, sizeof(SurfelSmem), s>>>(
-        W, H, gx, img, (const Surfel*)stream, capacity, bg, out_color, out_allmap, aux);
+        W, H, gx, gx * gy, img, (const Surfel*)stream, capacity, bg, out_color, out_allmap, aux);
     return cudaGetLastError();
 }
 
@@ -761,7 +782,7 @@ cudaError_t launch_surfel_blend_backward(int W, int H, ImageState img, const voi
                                          (int)sizeof(SurfelSmem));
     if (e != cudaSuccess) return e;
     surfel_blend_backward_kernel<<<gx * gy, SB_THREADS, sizeof(SurfelSmem), s>>>(
-        W, H, gx, img, (const Surfel*)stream, capacity, bg, out_allmap, aux, dL_dcolor, dL_dallmap, accum);
+        W, H, gx, gx * gy, img, (const Surfel*)stream, capacity, bg, out_allmap, aux, dL_dcolor, dL_dallmap, accum);
     return cudaGetLastError();
 }
 

@@ -1,52 +1,134 @@
-// Warp-cooperative iteration over the (Gaussian, tile) pairs owned by a warp.
+// Warp-cooperative binning of the (Gaussian, tile) pairs owned by a warp -- in ONE pass.
 //
-// Each lane owns one Gaussian covering an n = w*h tile rectangle (n may be 0).
-// Instead of each lane looping over its own rectangle (divergent trip counts,
-// one atomic per pair), the warp flattens all pairs into one index space and
-// walks it 32 at a time, so lanes stay busy regardless of how uneven the
-// rectangles are.  Callers then aggregate the bin-counter atomics per distinct
-// tile with __match_any_sync (one atomic per distinct tile per step): Gaussians
-// that are neighbours in memory are usually neighbours on screen (the model's
-// coarse Gaussians sit on a voxel grid in index order), so this removes most of
-// the same-address contention of the counters.
+// Replaces the reference's tiles_touched prefix sum + duplicateWithKeys
+// (RAST/cuda_rasterizer/rasterizer_impl.cu:278, 70-111) without a count pass: every kept pair claims the next
+// slot of its tile's key segment with one returning atomic on the tile's counter and writes its key
+// (depth bits << 32 | Gaussian index) there.  A tile's segment has a fixed capacity (ImageState / SortScratch in
+// state.cuh); claims beyond it are counted but not stored, and the host re-runs the frame with a larger capacity.
+//
+// Each lane owns one Gaussian covering an n = w*h tile rectangle (n may be 0).  Instead of each lane looping over
+// its own rectangle (divergent trip counts), the warp flattens all pairs into one index space and walks it 32 at a
+// time, so lanes stay busy regardless of how uneven the rectangles are:
+//   * the owners' parameters are parked once in a per-warp shared-memory table, compacted to the lanes with n > 0;
+//   * per step, the owners whose first pair falls into the 32-pair window raise one bit each (REDUX.OR), and a lane
+//     finds the owner of ITS pair with one popcount -- no binary search, no shuffles -- then reads the owner's
+//     record with four LDS.128 (SHFL issues at one warp-instruction per clock per SM on this part,
+//     profiles/r1_ubench.txt; the shuffle-based walk this replaces spent ~20 of them per step);
+//   * the key store of a step is issued one step later, so the returning atomic's round trip (ATOMG ~320 cycles
+//     unloaded) overlaps the next step's culling test.
 #pragma once
-#include "common.cuh"
+#include "state.cuh"
 
 namespace gdr {
 
-// f(tile_id, owner_lane, local_index, valid, active_mask, tile_x, tile_y); invoked by all 32 lanes each step.
-// local / w is a multiply-high by ceil(2^32 / w), computed once per lane (exact for local, w < 2^16): the
-// per-step integer divisions were a fifth of the walk.
-template <class F>
-__device__ __forceinline__ void warp_foreach_tile(int n, int x0, int y0, int w, int gx, F&& f) {
+// One owner (a lane with n > 0) of the warp's pair space.
+struct __align__(16) EmitRec {
+    float4 g0;  // centre x, y, reject threshold, conic a                  (culling test only)
+    float4 g1;  // conic b, c, -b / c, -b / a                               (culling test only)
+    uint4 r;    // first pair index (exclusive prefix), x0 | y0 << 16, w, ceil(2^32 / w)
+    uint2 key;  // Gaussian index, depth bits
+    uint2 pad;
+};
+static_assert(sizeof(EmitRec) == 64, "EmitRec must be 64 bytes");
+
+struct EmitTarget {
+    uint32_t* tile_count;  // [T] of this view
+    uint64_t* keys;        // [T][tile_cap] of this view
+    uint32_t tile_cap;
+    int gx;
+};
+
+// All 32 lanes call.  `kept` / `max_fill` accumulate this lane's binned pairs and the largest slot + 1 it claimed.
+// CULL: drop pairs whose tile the splat provably cannot reach with alpha >= 1/255 (splat_misses_rect, exact).
+template <bool CULL>
+__device__ __forceinline__ void warp_emit_tiles(EmitRec* __restrict__ s_rec, int n, int x0, int y0, int w, float4 q0,
+                                                float4 q1, uint32_t depth_bits, uint32_t idx, const EmitTarget& t,
+                                                uint32_t& kept, uint32_t& max_fill) {
     const unsigned full = 0xffffffffu;
-    const int lane = (int)lane_id();
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_lt();
     const int incl = warp_incl_scan(n);
     const int total = __shfl_sync(full, incl, 31);
-    const unsigned inv_w = w > 1 ? 0xffffffffu / (unsigned)w + 1u : 0u;  // w <= 1: rows are `local` itself
-    for (int base = 0; base < total; base += 32) {
-        const int j = base + lane;
-        int lo = 0, hi = 31;  // smallest lane whose inclusive prefix exceeds j
-#pragma unroll
-        for (int step = 0; step < 5; step++) {
-            const int mid = (lo + hi) >> 1;
-            const int v = __shfl_sync(full, incl, mid);
-            if (v > j) hi = mid; else lo = mid + 1;
+    if (total == 0) return;  // warp-uniform
+    const int excl = incl - n;
+    const unsigned owners = __ballot_sync(full, n > 0);
+    if (n > 0) {
+        EmitRec& r = s_rec[__popc(owners & lt)];
+        if (CULL) {
+            // (-b / c, -b / a): the same IEEE divisions splat_misses_rect performs, done once per splat
+            r.g0 = make_float4(q0.x, q0.y, q0.z, q1.x);
+            r.g1 = make_float4(q1.y, q1.z, __fdiv_rn(-q1.y, q1.z), __fdiv_rn(-q1.y, q1.x));
         }
-        const int owner = lo;
-        const int o_excl = __shfl_sync(full, incl - n, owner);
-        const int o_x0 = __shfl_sync(full, x0, owner);
-        const int o_y0 = __shfl_sync(full, y0, owner);
-        const int o_w = max(1, __shfl_sync(full, w, owner));
-        const unsigned o_inv = __shfl_sync(full, inv_w, owner);
-        const bool valid = j < total;
-        const int local = valid ? j - o_excl : 0;
-        const int row = o_w > 1 ? (int)__umulhi((unsigned)local, o_inv) : local;
-        const int tx = o_x0 + (local - row * o_w), ty = o_y0 + row;
-        const int tile = ty * gx + tx;
-        const unsigned active = __ballot_sync(full, valid);
-        f(tile, owner, local, valid, active, tx, ty);
+        // local / w as a multiply-high by ceil(2^32 / w) (exact for local, w < 2^16); w <= 1: the row is `local`
+        r.r = make_uint4((unsigned)excl, (unsigned)x0 | ((unsigned)y0 << 16), (unsigned)w,
+                         w > 1 ? 0xffffffffu / (unsigned)w + 1u : 0u);
+        r.key = make_uint2(idx, depth_bits);
     }
+    __syncwarp();
+    int o_start = 0;  // owners whose first pair lies before the current window
+    bool p_keep = false;  // the previous step's claim, stored one step late
+    uint32_t p_pos = 0;
+    size_t p_seg = 0;
+    uint2 p_key = make_uint2(0u, 0u);
+    for (int base = 0; base < total; base += 32) {
+        unsigned bit = 0;
+        if (n > 0 && excl >= base && excl < base + 32) bit = 1u << (excl - base);
+        const unsigned heads = __reduce_or_sync(full, bit);
+        const int j = base + (int)lane;
+        const bool valid = j < total;
+        // the owner of pair j is the last owner whose first pair is <= j (lanes past the end land on the last owner)
+        const int oc = o_start + __popc(heads & (lt | (1u << lane))) - 1;
+        o_start += __popc(heads);
+        const EmitRec& rec = s_rec[oc];
+        const uint4 rr = rec.r;
+        const int local = valid ? j - (int)rr.x : 0;
+        const int ow = (int)rr.z;
+        const int row = ow > 1 ? (int)__umulhi((unsigned)local, rr.w) : local;
+        const int tx = (int)(rr.y & 0xffffu) + (local - row * ow), ty = (int)(rr.y >> 16) + row;
+        const int tile = ty * t.gx + tx;
+        bool keep = valid;
+        if (CULL) {
+            const float4 g0 = rec.g0, g1 = rec.g1;
+            const float tx0 = (float)(tx * TILE), ty0 = (float)(ty * TILE);
+            keep = valid && !splat_misses_rect_pre(g0.x, g0.y, g0.w, g1.x, g1.y, g0.z, g1.z, g1.w, tx0, ty0,
+                                                   tx0 + (TILE - 1), ty0 + (TILE - 1));
+        }
+        uint32_t pos = 0;
+        if (keep) pos = atomicAdd(&t.tile_count[tile], 1u);
+        if (p_keep) {  // last step's key: its claim has had a whole step to come back
+            if (p_pos < t.tile_cap) t.keys[p_seg + p_pos] = ((uint64_t)p_key.y << 32) | p_key.x;
+            max_fill = max(max_fill, p_pos + 1u);
+        }
+        p_keep = keep;
+        p_pos = pos;
+        p_seg = (size_t)tile * t.tile_cap;
+        p_key = rec.key;
+        kept += keep ? 1u : 0u;
+    }
+    if (p_keep) {
+        if (p_pos < t.tile_cap) t.keys[p_seg + p_pos] = ((uint64_t)p_key.y << 32) | p_key.x;
+        max_fill = max(max_fill, p_pos + 1u);
+    }
+    __syncwarp();  // the table is rewritten by the warp's next batch of Gaussians
+}
+
+// The blend kernels' blockIdx -> tile map: tiles in decreasing-work order.  tile_sort files every tile under
+// bucket floor(log2(count)) + 1 (0 = empty); CTA i takes the i-th tile counting from the heaviest bucket down.
+// All 32 lanes call; every lane gets the tile.
+__device__ __forceinline__ int tile_from_order(const uint32_t* __restrict__ header, const uint32_t* __restrict__ order,
+                                               int T, int i) {
+    const unsigned full = 0xffffffffu;
+    const int lane = (int)lane_id();
+    const uint32_t cnt = header[HDR_BUCKET0 + 32 - lane];  // lane l owns bucket 32 - l: heaviest first
+    const int incl = warp_incl_scan((int)cnt);
+    const unsigned after = __ballot_sync(full, incl > i);
+    int b = 0, pos = i - __shfl_sync(full, incl, 31);  // bucket 0 (empty tiles) follows all the others
+    if (after) {
+        const int f = __ffs(after) - 1;
+        b = 32 - f;
+        pos = i - (__shfl_sync(full, incl, f) - (int)__shfl_sync(full, cnt, f));
+    }
+    return (int)order[(size_t)b * T + pos];
 }
 
 }  // namespace gdr

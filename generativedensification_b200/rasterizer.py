@@ -18,10 +18,11 @@ Differences from the reference that callers cannot observe through the returned
 tensors:
   * kernels run on torch's *current* stream (the reference uses the legacy default
     stream) and the host never drains the GPU: the instance count R is read from
-    pinned memory after an event that fires right after the tile scan, while the
-    rest of the frame is already enqueued with a predicted capacity; only a
-    mis-prediction (first call for a new scene size, or R grew by > 50 %) costs
-    a second `gdr_forward_render`;
+    pinned memory after an event that fires right after the projection kernel,
+    while the rest of the frame is already enqueued with predicted capacities; only
+    a mis-prediction (first call for a new scene size, R grew by > 50 %, or the
+    densest tile more than doubled) costs a second `gdr_forward_render` /
+    `gdr_forward_project`;
   * `ctx.needs_input_grad` is honoured (the reference computes every gradient
     every time); incoming `None` grads for depth / alpha are skipped instead of
     being materialised as zeros.
@@ -91,17 +92,32 @@ def round_capacity(n: int) -> int:
 
 
 class _CapacityPredictor:
-    """Remembers the last instance count per (device, P, H, W) to size the next frame's buffers."""
+    """Remembers the last instance count and the last largest per-tile count per (device, P, H, W, ...) to size the
+    next frame's buffers: the stream capacity (records) and the per-tile key-segment capacity (slots)."""
+
+    DEFAULT_TILE_CAPACITY = 2048
 
     def __init__(self):
         self.last = {}
+        self.last_tile = {}
 
     def predict(self, key) -> int:
         r = self.last.get(key)
         return 0 if r is None else round_capacity(int(r * 1.5) + 4096)
 
-    def update(self, key, r: int) -> None:
+    def predict_tile(self, key) -> int:
+        m = self.last_tile.get(key)
+        return self.DEFAULT_TILE_CAPACITY if m is None else round_tile_capacity(2 * m + 256)
+
+    def update(self, key, r: int, max_tile: int = 0) -> None:
         self.last[key] = r
+        self.last_tile[key] = max_tile
+
+
+def round_tile_capacity(n: int) -> int:
+    """Slots per tile segment: a multiple of 32 on the same coarse geometric grid as round_capacity (the key
+    segments are only touched where keys land, so headroom costs address space, not bandwidth)."""
+    return (round_capacity(max(int(n), 1)) + 31) // 32 * 32 if n > 1024 else 1024
 
 
 _predictor = _CapacityPredictor()
@@ -111,16 +127,56 @@ _predictor = _CapacityPredictor()
 options = {"tile_cull": os.environ.get("GDR_TILE_CULL", "1") != "0"}
 _mailboxes = {}
 
+PREFILTERED_MESSAGE = "Point is filtered although prefiltered is set. This shouldn't happen!"  # auxiliary.h:156
+
 
 def _mailbox(device) -> torch.Tensor:
-    """Small ring of pinned int32 slots the GPU writes R into."""
+    """Small ring of pinned int32 rows the GPU writes {R, flags, largest tile count, 0} into."""
     mb = _mailboxes.get(device)
     if mb is None:
-        mb = {"buf": torch.zeros(64, dtype=torch.int32).pin_memory(), "next": 0}
+        mb = {"buf": torch.zeros(64, 1, 4, dtype=torch.int32).pin_memory(), "next": 0}
         _mailboxes[device] = mb
     i = mb["next"]
     mb["next"] = (i + 1) % 64
-    return mb["buf"][i:i + 1]
+    return mb["buf"][i]
+
+
+def drive_forward(key, mailbox, stream, project, render):
+    """The host protocol shared by every forward entry (single view, batched views, surfels).
+
+    project(tile_capacity) enqueues the projection + binning kernel, whose counts land in `mailbox` (pinned
+    [V, 4] int32 rows {R, flags, largest per-tile count, 0}), and returns the key-segment scratch it allocated;
+    render(scratch, tile_capacity, capacity, rerun) enqueues tile sort + blend.  The render is enqueued
+    speculatively with the capacities predicted from the previous frame of the same `key`, then the host waits for
+    the projection kernel ONLY and repeats what a mis-prediction invalidated.  Returns the mailbox rows as lists."""
+    tile_cap = _predictor.predict_tile(key)
+    guess = _predictor.predict(key)
+    counted = torch.cuda.Event()
+    scratch = project(tile_cap)
+    counted.record(stream)
+    if guess > 0:
+        render(scratch, tile_cap, guess, False)  # speculative: the GPU keeps working while the host waits for R
+    counted.synchronize()  # waits for the projection kernel only, not for the frame
+    rows = mailbox.tolist()
+    rendered = guess > 0
+    max_tile = max(r[_lib.COUNT_MAX_TILE] for r in rows)
+    if max_tile > tile_cap:
+        # a tile received more instances than its key segment holds (first frame of a new scene size, or the
+        # densest tile more than doubled): the dropped keys are gone -- project again with room for them
+        tile_cap = round_tile_capacity(max_tile + max_tile // 4)
+        scratch = project(tile_cap)
+        counted.record(stream)
+        counted.synchronize()
+        rows = mailbox.tolist()
+        max_tile = max(r[_lib.COUNT_MAX_TILE] for r in rows)
+        rendered = False
+    r_max = max(r[_lib.COUNT_RENDERED] for r in rows)
+    _predictor.update(key, r_max, max_tile)
+    if not rendered:
+        render(scratch, tile_cap, round_capacity(r_max), False)
+    elif r_max > guess:
+        render(scratch, tile_cap, round_capacity(r_max), True)
+    return rows
 
 
 class _ForwardState:
@@ -171,42 +227,36 @@ def _forward_impl(settings: GaussianRasterizationSettings, means3D, sh, colors_p
         st.img = torch.empty(_lib.query_bytes("gdr_image_state_bytes", W, H), dtype=torch.uint8, device=device)
         mailbox = _mailbox(device)
         flags = 0 if options["tile_cull"] else _lib.FLAG_NO_TILE_CULL
-        _lib.check(lib.gdr_forward_project(
-            P, int(settings.sh_degree), st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
-            _ptr(scales), float(settings.scale_modifier), _ptr(rotations), _ptr(cov3Ds_precomp), _ptr(view),
-            _ptr(proj), _ptr(campos), float(settings.tanfovx), float(settings.tanfovy), int(bool(settings.prefiltered)),
-            radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(), mailbox.data_ptr(), flags, sptr),
-            "gdr_forward_project")
-        counted = torch.cuda.Event()
-        counted.record(stream)
-
+        key = (device.index, P, H, W, flags)
         color = torch.empty(3, H, W, **f32)
         depth = torch.empty(1, H, W, **f32)
         alpha = torch.empty(1, H, W, **f32)
 
-        def render(capacity: int):
+        def project(tile_capacity: int):
+            scratch = torch.empty(_lib.query_bytes("gdr_sort_scratch_bytes", W, H, tile_capacity), dtype=torch.uint8,
+                                  device=device)
+            _lib.check(lib.gdr_forward_project(
+                P, int(settings.sh_degree), st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp),
+                _ptr(opacities), _ptr(scales), float(settings.scale_modifier), _ptr(rotations), _ptr(cov3Ds_precomp),
+                _ptr(view), _ptr(proj), _ptr(campos), float(settings.tanfovx), float(settings.tanfovy),
+                int(bool(settings.prefiltered)), radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(),
+                scratch.data_ptr(), tile_capacity, mailbox.data_ptr(), flags, sptr), "gdr_forward_project")
+            return scratch
+
+        def render(scratch, tile_capacity: int, capacity: int, rerun: bool):
             st.capacity = capacity
             st.stream_buf = torch.empty(_lib.query_bytes("gdr_splat_stream_bytes", capacity), dtype=torch.uint8,
                                         device=device)
-            scratch = torch.empty(_lib.query_bytes("gdr_sort_scratch_bytes", capacity), dtype=torch.uint8,
-                                  device=device)
             _lib.check(lib.gdr_forward_render(
-                P, W, H, _ptr(bg), radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(), st.stream_buf.data_ptr(),
-                scratch.data_ptr(), capacity, color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), flags, sptr),
-                "gdr_forward_render")
+                P, W, H, _ptr(bg), st.geom.data_ptr(), st.img.data_ptr(), st.stream_buf.data_ptr(),
+                scratch.data_ptr(), tile_capacity, capacity, color.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
+                flags | (_lib.FLAG_RERUN if rerun else 0), sptr), "gdr_forward_render")
 
-        key = (device.index, P, H, W, flags)
-        guess = _predictor.predict(key)
-        if guess > 0:
-            render(guess)  # speculative: the GPU keeps working while the host waits for R
-        counted.synchronize()  # waits for project + tile scan only, not for the frame
-        R = int(mailbox.item())
-        _predictor.update(key, R)
-        st.num_rendered = R
-        if guess == 0 or R > guess:
-            render(round_capacity(R))
-        if settings.prefiltered:
-            pass  # the reference traps on-device if a prefiltered point is culled; we do not abort the context
+        rows = drive_forward(key, mailbox, stream, project, render)
+        st.num_rendered = rows[0][_lib.COUNT_RENDERED]
+        if settings.prefiltered and (rows[0][_lib.COUNT_FLAGS] & _lib.COUNT_FLAG_PREFILTERED):
+            # the reference printf()s this and traps on the device (auxiliary.h:154-158); here the context survives
+            raise RuntimeError(PREFILTERED_MESSAGE)
     return color, radii, depth, alpha, st
 
 

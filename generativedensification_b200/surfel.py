@@ -35,7 +35,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .rasterizer import _f32c, _mailbox, _ptr, round_capacity, _CapacityPredictor
+from .rasterizer import _f32c, _mailbox, _ptr, drive_forward
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -53,7 +53,6 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
-_predictor = _CapacityPredictor()
 
 
 class _SurfelState:
@@ -98,35 +97,31 @@ def _forward_impl(settings, means3D, sh, colors_precomp, opacities, scales, rota
         st.img = torch.empty(_lib.query_bytes("gdr_image_state_bytes", W, H), **u8)
         st.aux = torch.empty(_lib.query_bytes("gdr_surfel_aux_bytes", W, H), **u8)
         mailbox = _mailbox(device)
-        _lib.check(lib.gdr_surfel_forward_project(
-            P, int(settings.sh_degree), st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
-            _ptr(scales), st.scale_stride, float(settings.scale_modifier), _ptr(rotations), _ptr(transmat_precomp),
-            _ptr(view), _ptr(proj), _ptr(campos), radii.data_ptr(), st.geom.data_ptr(), st.surfel.data_ptr(),
-            st.img.data_ptr(), mailbox.data_ptr(), sptr), "gdr_surfel_forward_project")
-        counted = torch.cuda.Event()
-        counted.record(stream)
         color = torch.empty(3, H, W, **f32)
         allmap = torch.empty(7, H, W, **f32)
 
-        def render(capacity: int):
+        def project(tile_capacity: int):
+            scratch = torch.empty(_lib.query_bytes("gdr_sort_scratch_bytes", W, H, tile_capacity), **u8)
+            _lib.check(lib.gdr_surfel_forward_project(
+                P, int(settings.sh_degree), st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp),
+                _ptr(opacities), _ptr(scales), st.scale_stride, float(settings.scale_modifier), _ptr(rotations),
+                _ptr(transmat_precomp), _ptr(view), _ptr(proj), _ptr(campos), radii.data_ptr(), st.geom.data_ptr(),
+                st.surfel.data_ptr(), st.img.data_ptr(), scratch.data_ptr(), tile_capacity, mailbox.data_ptr(), sptr),
+                "gdr_surfel_forward_project")
+            return scratch
+
+        def render(scratch, tile_capacity: int, capacity: int, rerun: bool):
             st.capacity = capacity
             st.stream_buf = torch.empty(_lib.query_bytes("gdr_surfel_stream_bytes", capacity), **u8)
-            scratch = torch.empty(_lib.query_bytes("gdr_sort_scratch_bytes", capacity), **u8)
             _lib.check(lib.gdr_surfel_forward_render(
-                P, W, H, _ptr(bg), radii.data_ptr(), st.geom.data_ptr(), st.surfel.data_ptr(), st.img.data_ptr(),
-                st.stream_buf.data_ptr(), scratch.data_ptr(), capacity, color.data_ptr(), allmap.data_ptr(),
-                st.aux.data_ptr(), sptr), "gdr_surfel_forward_render")
+                P, W, H, _ptr(bg), st.geom.data_ptr(), st.surfel.data_ptr(), st.img.data_ptr(),
+                st.stream_buf.data_ptr(), scratch.data_ptr(), tile_capacity, capacity, color.data_ptr(),
+                allmap.data_ptr(), st.aux.data_ptr(), _lib.FLAG_RERUN if rerun else 0, sptr),
+                "gdr_surfel_forward_render")
 
-        key = (device.index, P, H, W)
-        guess = _predictor.predict(key)
-        if guess > 0:
-            render(guess)  # speculative, as in the 3DGS module: the GPU keeps working while the host learns R
-        counted.synchronize()
-        R = int(mailbox.item())
-        _predictor.update(key, R)
-        st.num_rendered = R
-        if guess == 0 or R > guess:
-            render(round_capacity(R))
+        # speculative, as in the 3DGS module: the GPU keeps working while the host learns the counts
+        rows = drive_forward((device.index, P, H, W, "surfel"), mailbox, stream, project, render)
+        st.num_rendered = rows[0][_lib.COUNT_RENDERED]
     return color, radii, allmap, st
 
 

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .rasterizer import GaussianRasterizationSettings, _f32c, _predictor, _ptr, options, round_capacity
+from .rasterizer import (PREFILTERED_MESSAGE, GaussianRasterizationSettings, _f32c, _ptr, drive_forward, options)
 
 
 class CameraBatch:
@@ -74,11 +74,11 @@ _pinned = {}
 
 
 def _mailbox_views(device, V: int) -> torch.Tensor:
-    """Ring of pinned int32 rows the GPU writes the per-view instance counts into."""
+    """Ring of pinned int32 [V, 4] blocks the GPU writes the per-view {R, flags, largest tile count, 0} into."""
     key = (device, V)
     mb = _pinned.get(key)
     if mb is None:
-        mb = {"buf": torch.zeros(8, V, dtype=torch.int32).pin_memory(), "next": 0}
+        mb = {"buf": torch.zeros(8, V, 4, dtype=torch.int32).pin_memory(), "next": 0}
         _pinned[key] = mb
     i = mb["next"]
     mb["next"] = (i + 1) % 8
@@ -122,40 +122,35 @@ def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scal
         flags = 0 if options["tile_cull"] else _lib.FLAG_NO_TILE_CULL
         if raw_params:
             flags |= _lib.FLAG_RAW_PARAMS
-        _lib.check(lib.gdr_views_forward_project(
-            V, P, cb.sh_degree, st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
-            _ptr(scales), cb.scale_modifier, _ptr(rotations), _ptr(cov3Ds_precomp), cb.cams.data_ptr(),
-            int(cb.prefiltered), radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(), mailbox.data_ptr(), flags,
-            sptr), "gdr_views_forward_project")
-        counted = torch.cuda.Event()
-        counted.record(stream)
-
         color = torch.empty(V, 3, H, W, **f32)
         depth = torch.empty(V, 1, H, W, **f32)
         alpha = torch.empty(V, 1, H, W, **f32)
+        one_view = _lib.query_bytes
 
-        def render(capacity: int):
+        def project(tile_capacity: int):
+            scratch = torch.empty(V * one_view("gdr_sort_scratch_bytes", W, H, tile_capacity), dtype=torch.uint8,
+                                  device=device)
+            _lib.check(lib.gdr_views_forward_project(
+                V, P, cb.sh_degree, st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
+                _ptr(scales), cb.scale_modifier, _ptr(rotations), _ptr(cov3Ds_precomp), cb.cams.data_ptr(),
+                int(cb.prefiltered), radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(), scratch.data_ptr(),
+                tile_capacity, mailbox.data_ptr(), flags, sptr), "gdr_views_forward_project")
+            return scratch
+
+        def render(scratch, tile_capacity: int, capacity: int, rerun: bool):
             st.capacity = capacity
             st.stream_buf = torch.empty(_lib.query_bytes("gdr_splat_stream_bytes", V * capacity), dtype=torch.uint8,
                                         device=device)
-            scratch = torch.empty(_lib.query_bytes("gdr_sort_scratch_bytes", V * capacity), dtype=torch.uint8,
-                                  device=device)
             _lib.check(lib.gdr_views_forward_render(
-                V, P, W, H, cb.cams.data_ptr(), radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(),
-                st.stream_buf.data_ptr(), scratch.data_ptr(), capacity, color.data_ptr(), depth.data_ptr(),
-                alpha.data_ptr(), flags, sptr), "gdr_views_forward_render")
+                V, P, W, H, cb.cams.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(), st.stream_buf.data_ptr(),
+                scratch.data_ptr(), tile_capacity, capacity, color.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
+                flags | (_lib.FLAG_RERUN if rerun else 0), sptr), "gdr_views_forward_render")
 
         key = (device.index, P, H, W, flags, "views", V)
-        guess = _predictor.predict(key)
-        if guess > 0:
-            render(guess)  # speculative: the GPU keeps working while the host waits for the counts
-        counted.synchronize()  # project + tile scan of all V views; ONE host wait per batch
-        counts = mailbox.tolist()
-        r_max = max(counts)
-        _predictor.update(key, r_max)
-        st.num_rendered = counts
-        if guess == 0 or r_max > guess:
-            render(round_capacity(r_max))
+        rows = drive_forward(key, mailbox, stream, project, render)  # ONE host wait per batch
+        st.num_rendered = [r[_lib.COUNT_RENDERED] for r in rows]
+        if cb.prefiltered and any(r[_lib.COUNT_FLAGS] & _lib.COUNT_FLAG_PREFILTERED for r in rows):
+            raise RuntimeError(PREFILTERED_MESSAGE)
     return color, radii, depth, alpha, st
 
 

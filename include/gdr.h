@@ -37,12 +37,16 @@
  * The forward is split in two so that the host never has to drain the GPU to
  * learn the instance count R (the reference blocks on a cudaMemcpy of it,
  * rasterizer_impl.cu:282):
- *   1. gdr_forward_project  -- per-Gaussian projection, tile counting, tile scan;
- *      enqueues an async copy of R into `num_rendered_host` (pinned memory).
- *   2. gdr_forward_render   -- instance emission, per-tile depth sort, blend; runs
- *      with a caller-chosen instance capacity.  If R turns out to exceed the
- *      capacity the kernels stay in bounds and the caller re-runs step 2 with a
- *      larger buffer (the Python shim does this speculatively).
+ *   1. gdr_forward_project  -- per-Gaussian projection AND binning in one kernel: every
+ *      (Gaussian, tile) instance claims a slot of its tile's key segment (`sort_scratch`,
+ *      `tile_capacity` slots per tile, chosen by the caller); enqueues an async copy of
+ *      {R, flags, largest per-tile count, 0} into `counts_host` (pinned memory).
+ *   2. gdr_forward_render   -- per-tile depth sort + record gather, blend; runs with a
+ *      caller-chosen stream capacity.
+ * Both capacities are predictions (the Python shim keeps the previous frame's values).  The
+ * kernels stay in bounds whatever they are; the caller compares the counts with what it
+ * passed and repeats step 1 (largest per-tile count > tile_capacity) or step 2
+ * (R > capacity, with GDR_FLAG_RERUN) with larger buffers.  See INTEGRATION.md.
  */
 #ifndef GDR_H_INCLUDED
 #define GDR_H_INCLUDED
@@ -64,7 +68,7 @@ extern "C" {
 #define GDR_ERR_CUDA (-2)
 #define GDR_ERR_UNSUPPORTED (-3)
 
-#define GDR_ABI_VERSION 1
+#define GDR_ABI_VERSION 2
 
 /* bit flags for gdr_backward(grad_mask): which input gradients the caller needs */
 #define GDR_GRAD_MEANS2D 1
@@ -85,6 +89,16 @@ extern "C" {
                                    `rotations` un-normalised quaternions; sigmoid / exp / normalise (what
                                    Renderer.render_img applies first, lightning/renderer.py:95-101, 225-230) run inside
                                    the projection kernel with torch's exact roundings.  gdr_forward_project only. */
+#define GDR_FLAG_RERUN 4        /* gdr_forward_render only: this render repeats an earlier one of the same projection
+                                   (larger capacity); resets the stream cursor and the tile order lists first */
+#define GDR_FLAG_FUSED_EPILOGUE 8 /* gdr_views_forward_render only: see that function */
+
+/* counts_host words written by gdr_forward_project (per view) */
+#define GDR_COUNT_RENDERED 0  /* R: instances binned */
+#define GDR_COUNT_FLAGS 1     /* GDR_COUNT_FLAG_* */
+#define GDR_COUNT_MAX_TILE 2  /* largest per-tile instance count; > tile_capacity => keys were dropped: re-run */
+#define GDR_COUNT_FLAG_PREFILTERED 2 /* prefiltered != 0 but a Gaussian failed the near-plane test (the reference traps
+                                        on the device here, auxiliary.h:154-158) */
 
 GDR_API int gdr_abi_version(void);
 GDR_API const char* gdr_last_error(void);
@@ -93,7 +107,9 @@ GDR_API const char* gdr_last_error(void);
 GDR_API int gdr_geom_state_bytes(int P, int64_t* bytes);              /* per-Gaussian state (reference: GeometryState) */
 GDR_API int gdr_image_state_bytes(int W, int H, int64_t* bytes);      /* per-pixel/per-tile state (reference: ImageState) */
 GDR_API int gdr_splat_stream_bytes(int64_t capacity, int64_t* bytes); /* depth-sorted per-tile instance stream, saved for backward */
-GDR_API int gdr_sort_scratch_bytes(int64_t capacity, int64_t* bytes); /* temporary, free after gdr_forward_render */
+GDR_API int gdr_sort_scratch_bytes(int W, int H, int64_t tile_capacity, int64_t* bytes); /* per view; temporary: tiles x
+                                                                         tile_capacity 8-byte keys (tile_capacity a positive
+                                                                         multiple of 32), free after gdr_forward_render */
 GDR_API int gdr_backward_scratch_bytes(int P, int64_t* bytes);        /* temporary screen-space gradient accumulators */
 
 /* Step 1 of the forward (replaces the first half of Rasterizer::forward, rasterizer_impl.cu:197-282). */
@@ -104,12 +120,14 @@ GDR_API int gdr_forward_project(int P, int sh_degree, int M, int W, int H,
                         const float* viewmatrix, const float* projmatrix, const float* campos,
                         float tan_fovx, float tan_fovy, int prefiltered,
                         int32_t* radii /* out [P] */, void* geom_state, void* image_state,
-                        int32_t* num_rendered_host /* pinned host memory or NULL */, int flags, void* stream);
+                        void* sort_scratch, int64_t tile_capacity,
+                        int32_t* counts_host /* pinned host memory [4] or NULL */, int flags, void* stream);
 
-/* Step 2 of the forward (replaces rasterizer_impl.cu:284-337). out_* are [3,H,W], [1,H,W], [1,H,W]. */
-GDR_API int gdr_forward_render(int P, int W, int H, const float* bg, const int32_t* radii,
+/* Step 2 of the forward (replaces rasterizer_impl.cu:304-337). out_* are [3,H,W], [1,H,W], [1,H,W].
+ * sort_scratch / tile_capacity are the ones step 1 filled. */
+GDR_API int gdr_forward_render(int P, int W, int H, const float* bg,
                        const void* geom_state, void* image_state,
-                       void* splat_stream, void* sort_scratch, int64_t capacity,
+                       void* splat_stream, void* sort_scratch, int64_t tile_capacity, int64_t capacity,
                        float* out_color, float* out_depth, float* out_alpha, int flags, void* stream);
 
 /* Backward (replaces Rasterizer::backward, rasterizer_impl.cu:343-447).  dL_dout_depth / dL_dout_alpha
@@ -142,8 +160,8 @@ GDR_API int gdr_mark_visible(int P, const float* means3D, const float* viewmatri
  * scale_modifier.  Per-view buffers are the single-view buffers repeated V times back to back:
  *     radii [V][P];  geom_states V * gdr_geom_state_bytes(P);  image_states V * gdr_image_state_bytes(W,H);
  *     splat_streams gdr_splat_stream_bytes(V * capacity_per_view)  (view v starts at record v * capacity);
- *     sort_scratch  gdr_sort_scratch_bytes(V * capacity_per_view);
- *     images [V][3|1][H][W];  num_rendered_host [V] (pinned);  backward_scratch gdr_backward_scratch_bytes(V * P).
+ *     sort_scratch  V * gdr_sort_scratch_bytes(W, H, tile_capacity);
+ *     images [V][3|1][H][W];  counts_host [V][4] (pinned);  backward_scratch gdr_backward_scratch_bytes(V * P).
  * gdr_views_backward SUMS the gradients of the shared Gaussians over the views (what autograd does when
  * the reference renders the views one by one from the same tensors), deterministically in view order. */
 typedef struct gdr_camera {
@@ -162,11 +180,12 @@ GDR_API int gdr_views_forward_project(int V, int P, int sh_degree, int M, int W,
                         const float* rotations, const float* cov3D_precomp,
                         const gdr_camera* cameras /* device [V] */, int prefiltered,
                         int32_t* radii /* out [V][P] */, void* geom_states, void* image_states,
-                        int32_t* num_rendered_host /* pinned [V] or NULL */, int flags, void* stream);
-GDR_API int gdr_views_forward_render(int V, int P, int W, int H, const gdr_camera* cameras, const int32_t* radii,
+                        void* sort_scratch, int64_t tile_capacity,
+                        int32_t* counts_host /* pinned [V][4] or NULL */, int flags, void* stream);
+GDR_API int gdr_views_forward_render(int V, int P, int W, int H, const gdr_camera* cameras,
                         const void* geom_states, void* image_states, void* splat_streams, void* sort_scratch,
-                        int64_t capacity_per_view, float* out_color /*[V,3,H,W]*/, float* out_depth /*[V,1,H,W]*/,
-                        float* out_alpha /*[V,1,H,W]*/, int flags, void* stream);
+                        int64_t tile_capacity, int64_t capacity_per_view, float* out_color /*[V,3,H,W]*/,
+                        float* out_depth /*[V,1,H,W]*/, float* out_alpha /*[V,1,H,W]*/, int flags, void* stream);
 GDR_API int gdr_views_backward(int V, int P, int sh_degree, int M, int W, int H,
                         const float* means3D, const float* shs, const float* colors_precomp,
                         const float* scales, float scale_modifier, const float* rotations,
@@ -224,13 +243,14 @@ GDR_API int gdr_surfel_forward_project(int P, int sh_degree, int M, int W, int H
                         const float* rotations, const float* transmat_precomp,
                         const float* viewmatrix, const float* projmatrix, const float* campos,
                         int32_t* radii /* out [P] */, void* geom_state, void* surfel_state, void* image_state,
-                        int32_t* num_rendered_host /* pinned host memory or NULL */, void* stream);
+                        void* sort_scratch, int64_t tile_capacity,
+                        int32_t* counts_host /* pinned host memory [4] or NULL */, void* stream);
 
-/* out_color [3,H,W], out_allmap [7,H,W]. */
-GDR_API int gdr_surfel_forward_render(int P, int W, int H, const float* bg, const int32_t* radii,
+/* out_color [3,H,W], out_allmap [7,H,W].  flags: 0 or GDR_FLAG_RERUN. */
+GDR_API int gdr_surfel_forward_render(int P, int W, int H, const float* bg,
                         const void* geom_state, const void* surfel_state, void* image_state,
-                        void* surfel_stream, void* sort_scratch, int64_t capacity,
-                        float* out_color, float* out_allmap, void* surfel_aux, void* stream);
+                        void* surfel_stream, void* sort_scratch, int64_t tile_capacity, int64_t capacity,
+                        float* out_color, float* out_allmap, void* surfel_aux, int flags, void* stream);
 
 /* dL_dout_allmap may be NULL (zero).  Any output pointer may be NULL; requested outputs are fully written.
  * dL_dmeans2D is [P, means2D_cols] (3 or 4): columns 0:2 = the densification statistic of 2DGS (gradient w.r.t. the
@@ -260,22 +280,23 @@ GDR_API int gdr_knn3_mean_dist2(int P, const float* points /*[P,3]*/, float* out
 GDR_API int gdr_debug_unpack_geom(int P, const void* geom_state, float* means2D /*[P,2]*/, float* depths /*[P]*/,
                           float* conic_opacity /*[P,4]*/, float* rgb /*[P,3]*/, float* cov3D /*[P,6]*/,
                           uint32_t* tiles_touched /*[P]*/, uint8_t* clamped /*[P,3]*/, void* stream);
-/* Sorted Gaussian ids per tile instance ([capacity] uint32) and tile ranges ([tiles,2] uint32). */
+/* Sorted Gaussian ids per tile instance ([capacity] uint32) and tile ranges ([tiles,2] uint32), both in the
+ * REFERENCE's layout (tiles in tile order, as its global sort leaves them, rasterizer_impl.cu:304-315) -- the stream
+ * itself keeps the tiles in completion order.  `ranges` is required when `point_list` is requested. */
 GDR_API int gdr_debug_unpack_bins(int W, int H, const void* image_state, const void* splat_stream, int64_t capacity,
                           uint32_t* point_list, uint32_t* ranges, uint32_t* n_contrib /*[H,W]*/, void* stream);
 
 /* Opt-in per-stage device timing for benchmarks (not used on the product path).  While enabled, every
  * kernel launch is bracketed by cudaEvents on the launch stream.  gdr_profile_read synchronises on the
  * recorded events, adds the elapsed milliseconds and launch counts per stage into the two arrays
- * (GDR_NUM_STAGES entries each) and clears the log.  Process-wide and not thread-safe. */
-#define GDR_STAGE_PROJECT 0
-#define GDR_STAGE_TILE_SCAN 1
-#define GDR_STAGE_EMIT 2
-#define GDR_STAGE_TILE_SORT 3
-#define GDR_STAGE_BLEND_FWD 4
-#define GDR_STAGE_BLEND_BWD 5
-#define GDR_STAGE_GAUSS_BWD 6
-#define GDR_NUM_STAGES 7
+ * (GDR_NUM_STAGES entries each) and clears the log.  This event log is the one piece of process-wide state in the
+ * library (guarded by a mutex: the forward and autograd's backward thread both append to it). */
+#define GDR_STAGE_PROJECT 0   /* projection + binning */
+#define GDR_STAGE_TILE_SORT 1
+#define GDR_STAGE_BLEND_FWD 2
+#define GDR_STAGE_BLEND_BWD 3
+#define GDR_STAGE_GAUSS_BWD 4
+#define GDR_NUM_STAGES 5
 GDR_API int gdr_profile_enable(int on);
 GDR_API int gdr_profile_read(double* stage_ms, int64_t* stage_launches);
 

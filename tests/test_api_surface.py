@@ -117,7 +117,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.gdr_abi_version() == 1
+    assert lib.gdr_abi_version() == 2
     # size queries are pure host functions
     assert _lib.query_bytes("gdr_geom_state_bytes", 1000) >= 1000 * (48 + 24 + 4 + 1)
     assert _lib.query_bytes("gdr_image_state_bytes", 800, 800) >= 800 * 800 * 4 + 2500 * 8
@@ -132,12 +132,16 @@ def test_library_exports_every_declared_symbol():
     assert _lib.query_bytes("gdr_surfel_state_bytes", 10) >= 800
     assert _lib.query_bytes("gdr_surfel_aux_bytes", 8, 8) >= 12 * 64
     nul = ctypes.c_void_p(None)
-    project_args = lambda P, img: (P, 1, 4, 64, 64, nul, nul, nul, nul, nul, 1.0, nul, nul, nul, nul, nul, 1.0, 1.0, 0,
-                                   nul, nul, img, nul, 0, nul)
+    project_args = lambda P, img, tile_cap=1024: (P, 1, 4, 64, 64, nul, nul, nul, nul, nul, 1.0, nul, nul, nul, nul, nul,
+                                                  1.0, 1.0, 0, nul, nul, img, nul, tile_cap, nul, 0, nul)
     assert lib.gdr_forward_project(*project_args(-1, nul)) == -1
     assert lib.gdr_forward_project(*project_args(1 << 28, nul)) == -3
     assert b"2^28" in lib.gdr_last_error()
     assert lib.gdr_forward_project(*project_args(10, nul)) == -1 and b"image_state" in lib.gdr_last_error()
+    # the per-tile key-segment capacity must be a positive multiple of 32
+    assert _lib.query_bytes("gdr_sort_scratch_bytes", 800, 800, 1024) == 2500 * 1024 * 8
+    assert raw.gdr_sort_scratch_bytes(800, 800, ctypes.c_int64(1000), ctypes.byref(out)) < 0
+    assert lib.gdr_forward_render(10, 64, 64, nul, nul, nul, nul, nul, 1024, 1 << 33, nul, nul, nul, 0, nul) == -1
     assert lib.gdr_surfel_backward(10, 1, 4, 64, 64, *([nul] * 3), nul, nul, 3, 1.0, *([nul] * 10), 0, *([nul] * 5), 5,
                                    *([nul] * 9)) == -1
 
@@ -157,10 +161,10 @@ def test_library_has_sm100a_code_and_tma_instructions():
     sass = subprocess.run([cuobjdump, "-sass", _lib.lib_path()], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass       # cp.async.bulk global->shared
     assert "SYNCS" in sass        # mbarrier
-    assert "MATCH" in sass        # warp-aggregated bin counters
+    assert "REDUX" in sass        # warp-wide integer reductions of the binning walk (owner heads, instance totals)
+    assert "ATOMG" in sass        # slot claims on the per-tile counters (returning atomics)
     assert "SHFL" in sass and "RED" in sass
     assert "FFMA2" in sass        # packed FP32 pairs in the blend kernels
-    assert "UCGABAR" in sass      # thread-block cluster barrier (tile_scan's 8-CTA cluster)
     assert "ACQBULK" in sass and "PREEXIT" in sass  # programmatic dependent launch (griddepcontrol.wait / .launch_dependents)
 
 

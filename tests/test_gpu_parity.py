@@ -186,6 +186,17 @@ def test_capacity_misprediction_is_rerun(device):
     c = _render(sc, device)
     for x, y in zip(a, c):
         assert torch.equal(x, y)
+    # a per-tile key segment far too small: the projection is repeated with room for the densest tile
+    assert Rz._predictor.last_tile[key] > 32
+    Rz._predictor.last_tile[key] = -100  # predicts the minimum...
+    old = Rz.round_tile_capacity
+    Rz.round_tile_capacity = lambda n: 32 if n <= 56 else old(n)  # ...which this makes 32 slots
+    try:
+        d = _render(sc, device)
+    finally:
+        Rz.round_tile_capacity = old
+    for x, y in zip(a, d):
+        assert torch.equal(x, y)
 
 
 def test_long_tile_lists_take_the_merge_path(device):

@@ -236,13 +236,13 @@ def test_benchmark_size_surfels_render_and_backpropagate(device):
 def test_capacity_misprediction_and_side_stream(device):
     """The surfel shim speculates on the instance count like the 3DGS one: a too-small prediction is re-run with the
     exact capacity, the cold path waits for R, and everything runs on torch's current stream -- same bits each time."""
-    from generativedensification_b200 import surfel as SF
+    from generativedensification_b200 import rasterizer as SF  # the predictor is shared with the 3DGS module
 
     sc = SCENES["s_deg1_ragged"]
     gc, ga = SU.surfel_upstream(sc)
     a = SU.run_ours(sc, device, grads=(gc, ga))
     P = sc["means3D"].shape[0]
-    key = (device.index, P, sc["camera"]["image_height"], sc["camera"]["image_width"])
+    key = (device.index, P, sc["camera"]["image_height"], sc["camera"]["image_width"], "surfel")
     assert SF._predictor.last[key] > 0
     SF._predictor.last[key] = 10
     b = SU.run_ours(sc, device, grads=(gc, ga))

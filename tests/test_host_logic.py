@@ -18,6 +18,13 @@ def test_capacity_predictor():
     assert p.predict(("k",)) >= 1500       # 50 % head-room
     p.update(("k",), 10)
     assert p.predict(("k",)) >= 15
+    # per-tile key-segment capacity: a default for a cold key, then 2x the last largest tile, multiples of 32
+    from generativedensification_b200.rasterizer import round_tile_capacity
+    assert p.predict_tile(("cold",)) == _CapacityPredictor.DEFAULT_TILE_CAPACITY
+    p.update(("k",), 1000, 3000)
+    assert p.predict_tile(("k",)) >= 6000 and p.predict_tile(("k",)) % 32 == 0
+    for n in (0, 1, 1024, 1025, 5000, 123457):
+        assert round_tile_capacity(n) >= max(n, 1024) and round_tile_capacity(n) % 32 == 0
 
 
 def test_shard_indices_cover_everything_once():

@@ -7,8 +7,8 @@ import json
 import subprocess
 import sys
 
-STAGE = {"project_kernel": "project", "tile_scan_kernel": "tile_scan", "emit_kernel": "emit", "tile_sort_kernel": "tile_sort",
-         "blend_forward_kernel": "blend_fwd", "blend_backward": "blend_bwd", "gauss_backward_kernel": "gauss_bwd"}
+STAGE = {"project_kernel": "project", "tile_sort_kernel": "tile_sort", "blend_forward_kernel": "blend_fwd",
+         "blend_backward": "blend_bwd", "gauss_backward_kernel": "gauss_bwd"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
