@@ -24,7 +24,7 @@ FLAG_NO_TILE_CULL = 1
 FLAG_RAW_PARAMS = 2
 FLAG_RERUN = 4
 FLAG_FUSED_EPILOGUE = 8
-COUNT_RENDERED, COUNT_FLAGS, COUNT_MAX_TILE = 0, 1, 2
+COUNT_RENDERED, COUNT_FLAGS, COUNT_MAX_TILE, COUNT_READY = 0, 1, 2, 3
 COUNT_FLAG_PREFILTERED = 2
 CAMERA_FLOATS = 48
 

@@ -142,6 +142,7 @@ int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, in
     if (P >= (1 << gdr::STREAM_REGION_SHIFT))
         return fail(GDR_ERR_UNSUPPORTED, "%s: at most 2^28 - 1 Gaussians per call", who);
     if (!image_state) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: image_state is NULL", who);
+    if (tiles_of(W, H) >= (1 << 24)) return fail(GDR_ERR_UNSUPPORTED, "%s: at most 2^24 - 1 tiles per image", who);
     if (P > 0) {
         if (!g.means3D || !g.opacities || !radii || !geom_state || !vw.view || !vw.proj)
             return fail(GDR_ERR_INVALID_ARGUMENT, "%s: a required pointer is NULL", who);
@@ -160,7 +161,7 @@ int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, in
     gdr::ImageState img = gdr::ImageState::carve(image_state, W, H);
     const int T = tiles_of(W, H);
     // header and per-tile slot counters are adjacent: one memset (strided over the views of a batch)
-    const size_t zero_bytes = (size_t)((char*)(img.tile_count + T) - (char*)img.header);
+    const size_t zero_bytes = (size_t)((char*)(img.tile_count + (size_t)T * gdr::COUNT_STRIDE) - (char*)img.header);
     if (vw.V == 1)
         GDR_CUDA(cudaMemsetAsync(img.header, 0, zero_bytes, s), "memset(header, tile_count)");
     else
@@ -184,15 +185,17 @@ int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, in
         a.keys = (uint64_t*)sort_scratch;
         a.keys_stride = gdr::sort_scratch_bytes(W, H, tile_capacity) / sizeof(uint64_t);
         a.tile_cap = (uint32_t)tile_capacity;
+        a.counts_host = counts_host;  // written by the kernel's last CTA: no copy node between it and tile_sort
         {
             StageTimer t(GDR_STAGE_PROJECT, s);
             GDR_CUDA(gdr::launch_project(a, s), "project");
         }
+    } else if (counts_host) {
+        for (int v = 0; v < vw.V; v++) {
+            counts_host[4 * v] = counts_host[4 * v + 1] = counts_host[4 * v + 2] = 0;
+            counts_host[4 * v + 3] = 1;
+        }
     }
-    if (counts_host)  // R, flags, largest tile count, 0 of every view
-        GDR_CUDA(cudaMemcpy2DAsync(counts_host, 4 * sizeof(int32_t), img.header, vw.V > 1 ? vw.img_stride : 4 * sizeof(int32_t),
-                                   4 * sizeof(int32_t), (size_t)vw.V, cudaMemcpyDeviceToHost, s),
-                 "memcpy(counts)");
     return GDR_OK;
 }
 
@@ -466,19 +469,19 @@ int gdr_surfel_forward_project(int P, int sh_degree, int M, int W, int H, const 
     }
     gdr::ImageState img = gdr::ImageState::carve(image_state, W, H);
     const int T = tiles_of(W, H);
-    GDR_CUDA(cudaMemsetAsync(img.header, 0, (size_t)((char*)(img.tile_count + T) - (char*)img.header), s),
+    GDR_CUDA(cudaMemsetAsync(img.header, 0, (size_t)((char*)(img.tile_count + (size_t)T * gdr::COUNT_STRIDE) - (char*)img.header), s),
              "memset(header, tile_count)");
     if (P > 0) {
         StageTimer t(GDR_STAGE_PROJECT, s);
         GDR_CUDA(gdr::launch_surfel_project(P, sh_degree, M, W, H, means3D, shs, colors_precomp, opacities, scales,
                                             scale_stride, scale_modifier, rotations, transmat_precomp, viewmatrix,
                                             projmatrix, campos, radii, gdr::GeomState::carve(geom_state, (size_t)P),
-                                            surfel_state, img, (uint64_t*)sort_scratch, tile_capacity, s),
+                                            surfel_state, img, (uint64_t*)sort_scratch, tile_capacity, counts_host, s),
                  "surfel_project");
+    } else if (counts_host) {
+        counts_host[0] = counts_host[1] = counts_host[2] = 0;
+        counts_host[3] = 1;
     }
-    if (counts_host)
-        GDR_CUDA(cudaMemcpyAsync(counts_host, img.header, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s),
-                 "memcpy(counts)");
     return GDR_OK;
 }
 

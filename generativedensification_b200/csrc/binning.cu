@@ -97,7 +97,7 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
     const ImageState img = img0.at(v, img_stride);
     float4* __restrict__ stream = stream0 + (size_t)v * capacity * RQ;
     const int tile = blockIdx.x;
-    const uint32_t n_binned = min(img.tile_count[tile], tile_cap);  // claims beyond the segment were not stored
+    const uint32_t n_binned = min(img.tile_count[(size_t)tile * COUNT_STRIDE], tile_cap);  // claims beyond the segment were not stored
     if (threadIdx.x == 0) {
         // the tile's range of the stream, and its place in the blend kernels' heaviest-first order
         uint32_t base = 0, n_fit = 0;
@@ -354,15 +354,7 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
             // bound the blend kernels would otherwise evaluate once per warp, in the forward AND the backward):
             // bit 28 + r of the id word.  Gaussian indices stay below 2^28 (checked at the API).
             const float tx0 = (float)((tile % gx) * TILE), ty0 = (float)((tile / gx) * TILE);
-            unsigned m = 0;
-            const float inv_c = __fdiv_rn(-w[1].y, w[1].z), inv_a = __fdiv_rn(-w[1].y, w[1].x);
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const float rx = tx0 + (float)((r & 1) * 8), ry = ty0 + (float)((r >> 1) * 8);
-                if (!splat_misses_rect_pre(w[0].x - rx, w[0].y - ry, w[1].x, w[1].y, w[1].z, w[0].z, inv_c, inv_a, 0.f,
-                                           0.f, 7.f, 7.f))
-                    m |= 1u << r;
-            }
+            const unsigned m = region_mask4(w[0].x - tx0, w[0].y - ty0, w[1].x, w[1].y, w[1].z, w[0].z);
             w[0].w = __uint_as_float(__float_as_uint(w[0].w) | (m << STREAM_REGION_SHIFT));
         }
         float4* dst4 = out + (size_t)i * RQ;

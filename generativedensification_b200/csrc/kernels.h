@@ -53,6 +53,7 @@ struct ProjectArgs {
     uint64_t* keys;      // [V][T][tile_cap] key segments (SortScratch, state.cuh)
     size_t keys_stride;  // keys between consecutive views
     uint32_t tile_cap;   // slots per tile segment
+    int32_t* counts_host;  // device-accessible pinned host memory [V][4] or nullptr (see report_counts)
 };
 
 // project.cu: per-Gaussian projection + warp-aggregated tile counting
@@ -124,7 +125,8 @@ cudaError_t launch_surfel_project(int P, int sh_degree, int M, int W, int H, con
                                   int scale_stride, float scale_modifier, const float* rotations,
                                   const float* transmat_precomp, const float* view, const float* proj,
                                   const float* campos, int32_t* radii, GeomState geom, void* surfel_state,
-                                  ImageState img, uint64_t* keys, int64_t tile_cap, cudaStream_t s);
+                                  ImageState img, uint64_t* keys, int64_t tile_cap, int32_t* counts_host,
+                                  cudaStream_t s);
 cudaError_t launch_surfel_blend_forward(int W, int H, ImageState img, const void* stream, int64_t capacity,
                                         const float* bg, float* out_color, float* out_allmap, float* aux,
                                         cudaStream_t s);

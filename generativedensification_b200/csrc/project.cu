@@ -33,20 +33,6 @@ __device__ constexpr float kSH3[7] = {-0.5900435899266435f, 2.890611442640554f, 
                                       0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
                                       -0.5900435899266435f};
 
-// Copy `count` floats from g (global) to s (shared) with 128-bit loads when the
-// source is 16-byte aligned, scalar loads otherwise.  All threads of the CTA call.
-__device__ __forceinline__ void stage_floats(float* s, const float* __restrict__ g, int count) {
-    if ((((uintptr_t)g) & 15u) == 0) {
-        const int n4 = count >> 2;
-        const float4* g4 = reinterpret_cast<const float4*>(g);
-        float4* s4 = reinterpret_cast<float4*>(s);
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) s4[i] = __ldg(g4 + i);
-        for (int i = (n4 << 2) + threadIdx.x; i < count; i += blockDim.x) s[i] = __ldg(g + i);
-    } else {
-        for (int i = threadIdx.x; i < count; i += blockDim.x) s[i] = __ldg(g + i);
-    }
-}
-
 // World covariance from scale + (un-normalised) quaternion: Sigma = (S R)^T (S R).
 // The roundings are pinned with explicit intrinsics: which product of x*z +- r*y etc. gets fused
 // into an FMA decides the last bit of the conic, and through it whether a pair sits above or
@@ -157,7 +143,7 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, float3 pos, float3 campos, 
 }
 
 __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs a) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     const int v = blockIdx.y;  // view of the batch
     const float* __restrict__ viewmatrix = a.vw.view + (size_t)v * a.vw.cam_stride;
     const float* __restrict__ projmatrix = a.vw.proj + (size_t)v * a.vw.cam_stride;
@@ -173,26 +159,56 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
     target.tile_cap = a.tile_cap;
     target.gx = a.gx;
     __shared__ uint32_t s_tot[2];
-    if (threadIdx.x == 0) s_tot[0] = s_tot[1] = 0u;
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        s_tot[0] = s_tot[1] = 0u;
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t parity = 0;
     uint32_t kept = 0, max_fill = 0;
+    const bool use_sh = a.colors_precomp == nullptr;
+    const bool use_scale = a.cov3D_precomp == nullptr;
+    // shared-memory slices of one virtual block (see the staging notes in common.cuh)
+    float* s_mean = smem;                          // 3 * PROJ_THREADS
+    float* s_scale = s_mean + 3 * PROJ_THREADS;    // 3 * PROJ_THREADS
+    float* s_sh = s_scale + 3 * PROJ_THREADS;      // 3 * M * PROJ_THREADS
+    float* s_splat = s_sh + 3 * (use_sh ? a.M : 0) * PROJ_THREADS;  // 12 * PROJ_THREADS: the block's Splat records
+    float* s_cov = s_splat + 12 * PROJ_THREADS;    // 6 * PROJ_THREADS: the block's world covariances
+    const int emit_offset_words = PROJ_THREADS * (6 + 12 + 6 + 3 * (use_sh ? a.M : 0));  // then one EmitRec per thread
+    // Full, 16-byte-aligned blocks move with the bulk-copy engine (one thread issues every slice: all in flight
+    // together, no per-thread copy loops); ragged or misaligned ones take the loops.
+    const bool aligned = ((((uintptr_t)a.means3D) | ((uintptr_t)a.scales) | ((uintptr_t)a.shs)) & 15u) == 0;
+    constexpr uint32_t ROW = sizeof(float) * PROJ_THREADS;  // bytes of one float per Gaussian
     const int n_vblocks = (a.P + PROJ_THREADS - 1) / PROJ_THREADS;
     for (int vb = blockIdx.x; vb < n_vblocks; vb += gridDim.x) {  // virtual blocks: balanced single wave
-    if (vb != (int)blockIdx.x) __syncthreads();                  // the staging buffers are reused
+    if (vb != (int)blockIdx.x) {
+        if (threadIdx.x == 0) bulk_wait_read();  // the previous block's records have left shared memory
+        __syncthreads();                         // the staging buffers are reused
+    }
     const int first = vb * PROJ_THREADS;
     const int n_items = min(PROJ_THREADS, a.P - first);
     const int idx = first + threadIdx.x;
     const bool in_range = threadIdx.x < n_items;
+    const bool bulk = aligned && n_items == PROJ_THREADS;
 
-    // ---- stage the 12-byte-stride inputs with coalesced 128-bit loads ----
-    float* s_mean = smem;                          // 3 * PROJ_THREADS
-    float* s_scale = s_mean + 3 * PROJ_THREADS;    // 3 * PROJ_THREADS
-    float* s_sh = s_scale + 3 * PROJ_THREADS;      // 3 * M * PROJ_THREADS
-    const int emit_offset_words = PROJ_THREADS * (6 + 3 * (a.colors_precomp ? 0 : a.M));  // then one EmitRec per thread
-    stage_floats(s_mean, a.means3D + (size_t)first * 3, n_items * 3);
-    if (a.cov3D_precomp == nullptr) stage_floats(s_scale, a.scales + (size_t)first * 3, n_items * 3);
-    const bool use_sh = a.colors_precomp == nullptr;
-    if (use_sh) stage_floats(s_sh, a.shs + (size_t)first * 3 * a.M, n_items * 3 * a.M);
-    __syncthreads();
+    // ---- stage the 12-byte-stride inputs ----
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, ROW * (3 + (use_scale ? 3 : 0) + (use_sh ? 3 * a.M : 0)));
+            bulk_g2s(s_mean, a.means3D + (size_t)first * 3, 3 * ROW, &bar);
+            if (use_scale) bulk_g2s(s_scale, a.scales + (size_t)first * 3, 3 * ROW, &bar);
+            if (use_sh) bulk_g2s(s_sh, a.shs + (size_t)first * 3 * a.M, 3 * a.M * ROW, &bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+    } else {
+        stage_floats(s_mean, a.means3D + (size_t)first * 3, n_items * 3);
+        if (use_scale) stage_floats(s_scale, a.scales + (size_t)first * 3, n_items * 3);
+        if (use_sh) stage_floats(s_sh, a.shs + (size_t)first * 3 * a.M, n_items * 3 * a.M);
+        __syncthreads();
+    }
 
     int n_tiles = 0, rx0 = 0, ry0 = 0, rw = 0;
     Splat rec;
@@ -273,14 +289,26 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
                                                                      // we flag, the host raises
         }
         radii[idx] = radius_out;
-        geom.splat[idx] = rec;
         geom.tiles_touched[idx] = (uint32_t)n_tiles;
         geom.clamped[idx] = (uint8_t)clamp_bits;
-        if (a.cov3D_precomp == nullptr) {
-            float2* c = reinterpret_cast<float2*>(geom.cov3D + (size_t)idx * 6);
+        // the 48-byte record and the 24-byte covariance: through shared memory for full blocks (they leave as two
+        // bulk stores below), directly otherwise
+        Splat* rec_dst = bulk ? reinterpret_cast<Splat*>(s_splat) + threadIdx.x : geom.splat + idx;
+        *rec_dst = rec;
+        if (use_scale) {
+            float2* c = reinterpret_cast<float2*>(bulk ? s_cov + 6 * threadIdx.x : geom.cov3D + (size_t)idx * 6);
             c[0] = make_float2(cov3D[0], cov3D[1]);
             c[1] = make_float2(cov3D[2], cov3D[3]);
             c[2] = make_float2(cov3D[4], cov3D[5]);
+        }
+    }
+    if (bulk) {
+        fence_async_smem();  // this thread's rows -> visible to the bulk-copy engine
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_s2g(geom.splat + first, s_splat, 12 * ROW);
+            if (use_scale) bulk_s2g(geom.cov3D + (size_t)first * 6, s_cov, 6 * ROW);
+            bulk_commit();
         }
     }
 
@@ -307,6 +335,8 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
     if (threadIdx.x == 0) {
         if (s_tot[0]) atomicAdd(&img.header[HDR_NUM_RENDERED], s_tot[0]);
         if (s_tot[1]) atomicMax(&img.header[HDR_MAX_TILE], s_tot[1]);
+        bulk_wait_all();  // this CTA's record / covariance stores are performed before it reports and exits
+        if (a.counts_host) report_counts(img.header, a.counts_host + 4 * v, gridDim.x);
     }
     pdl_trigger();  // tile_sort may start launching
 }
@@ -342,7 +372,7 @@ int sm_count() {
 
 cudaError_t launch_project(const ProjectArgs& a, cudaStream_t s) {
     if (a.P <= 0) return cudaSuccess;
-    const size_t smem = sizeof(float) * PROJ_THREADS * (6 + 3 * (size_t)(a.colors_precomp ? 0 : a.M)) +
+    const size_t smem = sizeof(float) * PROJ_THREADS * (6 + 12 + 6 + 3 * (size_t)(a.colors_precomp ? 0 : a.M)) +
                         sizeof(EmitRec) * PROJ_THREADS;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

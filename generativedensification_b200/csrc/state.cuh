@@ -7,8 +7,11 @@
 //     uint8    clamped[P]         1 B   bit c set <=> SH colour channel c was clamped at 0
 // ImageState (reference: ImageState + the per-tile half of BinningState, rasterizer_impl.h:50-66) -- per view:
 //     uint32   header[64]               see the HDR_* words below
-//     uint32   tile_count[T]            instances binned to each tile: the projection kernel claims a tile's slots with
-//                                       returning atomics on this counter (no count pass, no prefix sum)
+//     uint32   tile_count[T * COUNT_STRIDE]  instances binned to each tile (word t * COUNT_STRIDE): the projection kernel
+//                                       claims a tile's slots with returning atomics on this counter (no count pass, no
+//                                       prefix sum).  One counter per 256 bytes: the L2 atomic units serialise per
+//                                       line, and with 32 counters per 128-byte line ALL the frame's claims funnelled
+//                                       through T / 32 lines (measured: the projection kernel's time was flat in P)
 //     uint2    tile_range[T]            [begin, end) of the tile's depth-sorted records in the stream; tile_sort
 //                                       allocates it from a global cursor, so tiles lie in completion order -- nothing
 //                                       downstream needs them in tile order (the reference's `ranges` likewise only
@@ -67,12 +70,14 @@ struct GeomState {
 };
 
 constexpr int IMG_HEADER_WORDS = 64;
+constexpr int COUNT_STRIDE = 64;    // words between consecutive tiles' slot counters (256 B: see ImageState)
 constexpr int ORDER_BUCKETS = 33;   // floor(log2(count)) + 1 for count > 0, bucket 0 = empty tiles
 // header words.  The first four are what the host reads back (gdr_forward_project's counts_host); words from
 // HDR_CURSOR on belong to tile_sort and are reset when a render is repeated with a larger stream capacity.
 constexpr int HDR_NUM_RENDERED = 0;  // R: instances binned (after tile culling), summed by the projection kernel
 constexpr int HDR_PROJECT_FLAGS = 1; // HDR_FLAG_PREFILTERED
 constexpr int HDR_MAX_TILE = 2;      // largest per-tile instance count (may exceed the tile capacity: then re-run)
+constexpr int HDR_TICKET = 3;        // CTAs of the projection kernel that have finished (the last one reports the counts)
 constexpr int HDR_CURSOR = 4;        // tile_sort's stream allocation cursor
 constexpr int HDR_SORT_FLAGS = 5;    // HDR_FLAG_STREAM_OVERFLOW
 constexpr int HDR_BUCKET0 = 8;       // ORDER_BUCKETS fill counts of the order lists
@@ -93,7 +98,7 @@ struct ImageState {
         const size_t T = tiles(W, H);
         size_t o = 0;
         o = align_up(o + 4 * IMG_HEADER_WORDS, 256);
-        o = align_up(o + 4 * T, 256);
+        o = align_up(o + 4 * T * COUNT_STRIDE, 256);
         o = align_up(o + 8 * T, 256);
         o = align_up(o + 4 * T * ORDER_BUCKETS, 256);
         o = align_up(o + 4 * (size_t)W * H, 256);
@@ -107,7 +112,7 @@ struct ImageState {
         s.header = (uint32_t*)(p + o);
         o = align_up(o + 4 * IMG_HEADER_WORDS, 256);
         s.tile_count = (uint32_t*)(p + o);
-        o = align_up(o + 4 * T, 256);
+        o = align_up(o + 4 * T * COUNT_STRIDE, 256);
         s.tile_range = (uint2*)(p + o);
         o = align_up(o + 8 * T, 256);
         s.order = (uint32_t*)(p + o);

@@ -14,8 +14,8 @@
 //     finds the owner of ITS pair with one popcount -- no binary search, no shuffles -- then reads the owner's
 //     record with four LDS.128 (SHFL issues at one warp-instruction per clock per SM on this part,
 //     profiles/r1_ubench.txt; the shuffle-based walk this replaces spent ~20 of them per step);
-//   * the key store of a step is issued one step later, so the returning atomic's round trip (ATOMG ~320 cycles
-//     unloaded) overlaps the next step's culling test.
+//   * the slot claims of up to EMIT_DEPTH windows are issued before the first key is stored, so the returning
+//     atomics' round trips (ATOMG ~320 cycles unloaded) overlap each other and the culling tests.
 #pragma once
 #include "state.cuh"
 
@@ -31,9 +31,11 @@ struct __align__(16) EmitRec {
 };
 static_assert(sizeof(EmitRec) == 64, "EmitRec must be 64 bytes");
 
+constexpr int EMIT_DEPTH = 8;  // 32-pair windows whose slot claims are in flight together
+
 struct EmitTarget {
-    uint32_t* tile_count;  // [T] of this view
-    uint64_t* keys;        // [T][tile_cap] of this view
+    uint32_t* tile_count;  // [T * COUNT_STRIDE] of this view
+    uint64_t* keys;        // [T][tile_cap] of this view; T < 2^24 (checked at the API)
     uint32_t tile_cap;
     int gx;
 };
@@ -66,50 +68,70 @@ __device__ __forceinline__ void warp_emit_tiles(EmitRec* __restrict__ s_rec, int
     }
     __syncwarp();
     int o_start = 0;  // owners whose first pair lies before the current window
-    bool p_keep = false;  // the previous step's claim, stored one step late
-    uint32_t p_pos = 0;
-    size_t p_seg = 0;
-    uint2 p_key = make_uint2(0u, 0u);
-    for (int base = 0; base < total; base += 32) {
-        unsigned bit = 0;
-        if (n > 0 && excl >= base && excl < base + 32) bit = 1u << (excl - base);
-        const unsigned heads = __reduce_or_sync(full, bit);
-        const int j = base + (int)lane;
-        const bool valid = j < total;
-        // the owner of pair j is the last owner whose first pair is <= j (lanes past the end land on the last owner)
-        const int oc = o_start + __popc(heads & (lt | (1u << lane))) - 1;
-        o_start += __popc(heads);
-        const EmitRec& rec = s_rec[oc];
-        const uint4 rr = rec.r;
-        const int local = valid ? j - (int)rr.x : 0;
-        const int ow = (int)rr.z;
-        const int row = ow > 1 ? (int)__umulhi((unsigned)local, rr.w) : local;
-        const int tx = (int)(rr.y & 0xffffu) + (local - row * ow), ty = (int)(rr.y >> 16) + row;
-        const int tile = ty * t.gx + tx;
-        bool keep = valid;
-        if (CULL) {
-            const float4 g0 = rec.g0, g1 = rec.g1;
-            const float tx0 = (float)(tx * TILE), ty0 = (float)(ty * TILE);
-            keep = valid && !splat_misses_rect_pre(g0.x, g0.y, g0.w, g1.x, g1.y, g0.z, g1.z, g1.w, tx0, ty0,
-                                                   tx0 + (TILE - 1), ty0 + (TILE - 1));
+    // EMIT_DEPTH windows per round: all their slot claims are issued before the first key is stored, so a warp
+    // waits for ONE atomic round trip per round instead of one per window (ncu on the one-window-at-a-time
+    // version: 56 % of the kernel's stall samples sat on the claim's return value).
+    for (int g0 = 0; g0 < total; g0 += 32 * EMIT_DEPTH) {
+        uint32_t pos[EMIT_DEPTH], where[EMIT_DEPTH];  // claimed slot; tile | owner << 24, or ~0 for "no pair"
+#pragma unroll
+        for (int s = 0; s < EMIT_DEPTH; s++) {
+            pos[s] = 0;
+            where[s] = 0xffffffffu;
+            const int base = g0 + 32 * s;
+            if (base < total) {  // warp-uniform
+                unsigned bit = 0;
+                if (n > 0 && excl >= base && excl < base + 32) bit = 1u << (excl - base);
+                const unsigned heads = __reduce_or_sync(full, bit);
+                const int j = base + (int)lane;
+                const bool valid = j < total;
+                // the owner of pair j is the last owner whose first pair is <= j (lanes past the end: the last owner)
+                const int oc = o_start + __popc(heads & (lt | (1u << lane))) - 1;
+                o_start += __popc(heads);
+                const EmitRec& rec = s_rec[oc];
+                const uint4 rr = rec.r;
+                const int local = valid ? j - (int)rr.x : 0;
+                const int ow = (int)rr.z;
+                const int row = ow > 1 ? (int)__umulhi((unsigned)local, rr.w) : local;
+                const int tx = (int)(rr.y & 0xffffu) + (local - row * ow), ty = (int)(rr.y >> 16) + row;
+                const int tile = ty * t.gx + tx;
+                bool keep = valid;
+                if (CULL) {
+                    const float4 g0v = rec.g0, g1v = rec.g1;
+                    const float tx0 = (float)(tx * TILE), ty0 = (float)(ty * TILE);
+                    keep = valid && !splat_misses_rect_pre(g0v.x, g0v.y, g0v.w, g1v.x, g1v.y, g0v.z, g1v.z, g1v.w, tx0,
+                                                           ty0, tx0 + (TILE - 1), ty0 + (TILE - 1));
+                }
+                if (keep) {
+                    pos[s] = atomicAdd(&t.tile_count[(size_t)tile * COUNT_STRIDE], 1u);
+                    where[s] = (unsigned)tile | ((unsigned)oc << 24);
+                }
+            }
         }
-        uint32_t pos = 0;
-        if (keep) pos = atomicAdd(&t.tile_count[tile], 1u);
-        if (p_keep) {  // last step's key: its claim has had a whole step to come back
-            if (p_pos < t.tile_cap) t.keys[p_seg + p_pos] = ((uint64_t)p_key.y << 32) | p_key.x;
-            max_fill = max(max_fill, p_pos + 1u);
+#pragma unroll
+        for (int s = 0; s < EMIT_DEPTH; s++) {
+            if (where[s] != 0xffffffffu) {
+                const uint2 key = s_rec[where[s] >> 24].key;
+                if (pos[s] < t.tile_cap)
+                    t.keys[(size_t)(where[s] & 0xffffffu) * t.tile_cap + pos[s]] = ((uint64_t)key.y << 32) | key.x;
+                max_fill = max(max_fill, pos[s] + 1u);
+                kept += 1u;
+            }
         }
-        p_keep = keep;
-        p_pos = pos;
-        p_seg = (size_t)tile * t.tile_cap;
-        p_key = rec.key;
-        kept += keep ? 1u : 0u;
-    }
-    if (p_keep) {
-        if (p_pos < t.tile_cap) t.keys[p_seg + p_pos] = ((uint64_t)p_key.y << 32) | p_key.x;
-        max_fill = max(max_fill, p_pos + 1u);
     }
     __syncwarp();  // the table is rewritten by the warp's next batch of Gaussians
+}
+
+// Called by one thread per CTA of a projection kernel after its header atomics: the last CTA of the view to arrive
+// writes {R, flags, largest tile count} into the view's pinned host row and then sets word 3 (release, system scope)
+// -- the host polls that word (see st_host_release in common.cuh).
+__device__ __forceinline__ void report_counts(uint32_t* header, int32_t* counts_host, unsigned n_ctas) {
+    __threadfence();  // this CTA's header atomics are ordered before its ticket
+    if (atomicAdd(&header[HDR_TICKET], 1u) != n_ctas - 1) return;
+    __threadfence();
+    st_host_relaxed(counts_host + 0, (int32_t)ld_device_acquire(&header[HDR_NUM_RENDERED]));
+    st_host_relaxed(counts_host + 1, (int32_t)ld_device_acquire(&header[HDR_PROJECT_FLAGS]));
+    st_host_relaxed(counts_host + 2, (int32_t)ld_device_acquire(&header[HDR_MAX_TILE]));
+    st_host_release(counts_host + 3, 1);
 }
 
 // The blend kernels' blockIdx -> tile map: tiles in decreasing-work order.  tile_sort files every tile under

@@ -130,44 +130,75 @@ _mailboxes = {}
 PREFILTERED_MESSAGE = "Point is filtered although prefiltered is set. This shouldn't happen!"  # auxiliary.h:156
 
 
-def _mailbox(device) -> torch.Tensor:
-    """Small ring of pinned int32 rows the GPU writes {R, flags, largest tile count, 0} into."""
-    mb = _mailboxes.get(device)
+class Mailbox:
+    """One pinned [V, 4] int32 block {R, flags, largest tile count, ready} per view that the projection kernel's last
+    CTA writes directly (no copy node in the stream); the host polls the ready words."""
+    __slots__ = ("tensor", "words", "ptr")
+
+    def __init__(self, tensor: torch.Tensor):
+        self.tensor = tensor
+        self.words = tensor.numpy()  # shares the pinned memory: polling it is a plain host load
+        self.ptr = tensor.data_ptr()
+
+    def reset(self) -> None:
+        self.words[:, _lib.COUNT_READY] = 0
+
+    def wait(self, stream) -> list:
+        """Spin until every view's ready word is set; returns the rows as lists.  Checks the stream now and then
+        so that a failed launch raises instead of spinning forever."""
+        ready = self.words[:, _lib.COUNT_READY]
+        spins = 0
+        while not ready.all():
+            spins += 1
+            if spins % 4096 == 0 and stream.query():  # everything enqueued has finished...
+                if ready.all():
+                    break
+                raise RuntimeError("the projection kernel finished without reporting its counts")
+        return self.words.tolist()
+
+
+_mailboxes = {}
+
+
+def _mailbox(device, V: int = 1) -> Mailbox:
+    """Next block of a small ring of pinned mailboxes (a ring: a block is still being written by the GPU when the
+    previous call returns early on a mis-prediction path)."""
+    mb = _mailboxes.get((device, V))
     if mb is None:
-        mb = {"buf": torch.zeros(64, 1, 4, dtype=torch.int32).pin_memory(), "next": 0}
-        _mailboxes[device] = mb
+        buf = torch.zeros(32, V, 4, dtype=torch.int32).pin_memory()
+        mb = {"ring": [Mailbox(buf[i]) for i in range(32)], "next": 0}
+        _mailboxes[(device, V)] = mb
     i = mb["next"]
-    mb["next"] = (i + 1) % 64
-    return mb["buf"][i]
+    mb["next"] = (i + 1) % 32
+    return mb["ring"][i]
 
 
-def drive_forward(key, mailbox, stream, project, render):
+def drive_forward(key, mailbox: Mailbox, stream, project, render):
     """The host protocol shared by every forward entry (single view, batched views, surfels).
 
-    project(tile_capacity) enqueues the projection + binning kernel, whose counts land in `mailbox` (pinned
-    [V, 4] int32 rows {R, flags, largest per-tile count, 0}), and returns the key-segment scratch it allocated;
-    render(scratch, tile_capacity, capacity, rerun) enqueues tile sort + blend.  The render is enqueued
-    speculatively with the capacities predicted from the previous frame of the same `key`, then the host waits for
-    the projection kernel ONLY and repeats what a mis-prediction invalidated.  Returns the mailbox rows as lists."""
+    project(tile_capacity) enqueues the projection + binning kernel, whose last CTA writes the counts into
+    `mailbox`, and returns the key-segment scratch it allocated; render(scratch, tile_capacity, capacity, rerun)
+    enqueues tile sort + blend.  The render is enqueued speculatively with the capacities predicted from the
+    previous frame of the same `key`, then the host polls for the projection kernel's counts ONLY and repeats what
+    a mis-prediction invalidated.  Returns the mailbox rows as lists."""
     tile_cap = _predictor.predict_tile(key)
     guess = _predictor.predict(key)
-    counted = torch.cuda.Event()
+    mailbox.reset()
     scratch = project(tile_cap)
-    counted.record(stream)
     if guess > 0:
         render(scratch, tile_cap, guess, False)  # speculative: the GPU keeps working while the host waits for R
-    counted.synchronize()  # waits for the projection kernel only, not for the frame
-    rows = mailbox.tolist()
+    rows = mailbox.wait(stream)  # the projection kernel only, not the frame
     rendered = guess > 0
     max_tile = max(r[_lib.COUNT_MAX_TILE] for r in rows)
+    stats["forwards"] += 1
     if max_tile > tile_cap:
         # a tile received more instances than its key segment holds (first frame of a new scene size, or the
         # densest tile more than doubled): the dropped keys are gone -- project again with room for them
+        stats["reprojected"] += 1
         tile_cap = round_tile_capacity(max_tile + max_tile // 4)
+        mailbox.reset()
         scratch = project(tile_cap)
-        counted.record(stream)
-        counted.synchronize()
-        rows = mailbox.tolist()
+        rows = mailbox.wait(stream)
         max_tile = max(r[_lib.COUNT_MAX_TILE] for r in rows)
         rendered = False
     r_max = max(r[_lib.COUNT_RENDERED] for r in rows)
@@ -175,8 +206,13 @@ def drive_forward(key, mailbox, stream, project, render):
     if not rendered:
         render(scratch, tile_cap, round_capacity(r_max), False)
     elif r_max > guess:
+        stats["rerendered"] += 1
         render(scratch, tile_cap, round_capacity(r_max), True)
     return rows
+
+
+# how often the speculation failed (tests and tools read these)
+stats = {"forwards": 0, "reprojected": 0, "rerendered": 0}
 
 
 class _ForwardState:
@@ -240,7 +276,7 @@ def _forward_impl(settings: GaussianRasterizationSettings, means3D, sh, colors_p
                 _ptr(opacities), _ptr(scales), float(settings.scale_modifier), _ptr(rotations), _ptr(cov3Ds_precomp),
                 _ptr(view), _ptr(proj), _ptr(campos), float(settings.tanfovx), float(settings.tanfovy),
                 int(bool(settings.prefiltered)), radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(),
-                scratch.data_ptr(), tile_capacity, mailbox.data_ptr(), flags, sptr), "gdr_forward_project")
+                scratch.data_ptr(), tile_capacity, mailbox.ptr, flags, sptr), "gdr_forward_project")
             return scratch
 
         def render(scratch, tile_capacity: int, capacity: int, rerun: bool):

@@ -106,7 +106,7 @@ def _forward_impl(settings, means3D, sh, colors_precomp, opacities, scales, rota
                 P, int(settings.sh_degree), st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp),
                 _ptr(opacities), _ptr(scales), st.scale_stride, float(settings.scale_modifier), _ptr(rotations),
                 _ptr(transmat_precomp), _ptr(view), _ptr(proj), _ptr(campos), radii.data_ptr(), st.geom.data_ptr(),
-                st.surfel.data_ptr(), st.img.data_ptr(), scratch.data_ptr(), tile_capacity, mailbox.data_ptr(), sptr),
+                st.surfel.data_ptr(), st.img.data_ptr(), scratch.data_ptr(), tile_capacity, mailbox.ptr, sptr),
                 "gdr_surfel_forward_project")
             return scratch
 

@@ -25,7 +25,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .rasterizer import (PREFILTERED_MESSAGE, GaussianRasterizationSettings, _f32c, _ptr, drive_forward, options)
+from .rasterizer import (PREFILTERED_MESSAGE, GaussianRasterizationSettings, _f32c, _mailbox, _ptr, drive_forward,
+                         options)
 
 
 class CameraBatch:
@@ -70,21 +71,6 @@ class CameraBatch:
         return CameraBatch(cams, s0.image_height, s0.image_width, s0.sh_degree, s0.scale_modifier, s0.prefiltered)
 
 
-_pinned = {}
-
-
-def _mailbox_views(device, V: int) -> torch.Tensor:
-    """Ring of pinned int32 [V, 4] blocks the GPU writes the per-view {R, flags, largest tile count, 0} into."""
-    key = (device, V)
-    mb = _pinned.get(key)
-    if mb is None:
-        mb = {"buf": torch.zeros(8, V, 4, dtype=torch.int32).pin_memory(), "next": 0}
-        _pinned[key] = mb
-    i = mb["next"]
-    mb["next"] = (i + 1) % 8
-    return mb["buf"][i]
-
-
 class _ViewsState:
     __slots__ = ("geom", "img", "stream_buf", "capacity", "num_rendered", "P", "M", "V")
 
@@ -118,7 +104,7 @@ def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scal
         sptr = C.c_void_p(stream.cuda_stream)
         st.geom = torch.empty(V * _lib.query_bytes("gdr_geom_state_bytes", P), dtype=torch.uint8, device=device)
         st.img = torch.empty(V * _lib.query_bytes("gdr_image_state_bytes", W, H), dtype=torch.uint8, device=device)
-        mailbox = _mailbox_views(device, V)
+        mailbox = _mailbox(device, V)
         flags = 0 if options["tile_cull"] else _lib.FLAG_NO_TILE_CULL
         if raw_params:
             flags |= _lib.FLAG_RAW_PARAMS
@@ -134,7 +120,7 @@ def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scal
                 V, P, cb.sh_degree, st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
                 _ptr(scales), cb.scale_modifier, _ptr(rotations), _ptr(cov3Ds_precomp), cb.cams.data_ptr(),
                 int(cb.prefiltered), radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(), scratch.data_ptr(),
-                tile_capacity, mailbox.data_ptr(), flags, sptr), "gdr_views_forward_project")
+                tile_capacity, mailbox.ptr, flags, sptr), "gdr_views_forward_project")
             return scratch
 
         def render(scratch, tile_capacity: int, capacity: int, rerun: bool):

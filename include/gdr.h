@@ -93,10 +93,14 @@ extern "C" {
                                    (larger capacity); resets the stream cursor and the tile order lists first */
 #define GDR_FLAG_FUSED_EPILOGUE 8 /* gdr_views_forward_render only: see that function */
 
-/* counts_host words written by gdr_forward_project (per view) */
+/* counts_host: 4 int32 per view in PINNED host memory that the device can address (cudaHostAlloc / cudaHostRegister,
+ * unified addressing).  The projection kernel's last CTA stores words 0..2 and then word 3 = 1 with release / system
+ * semantics: the caller zeroes word 3 before the call and polls it (or waits for the stream) -- no copy node or event
+ * sits between the projection kernel and the kernels that follow it in the stream. */
 #define GDR_COUNT_RENDERED 0  /* R: instances binned */
 #define GDR_COUNT_FLAGS 1     /* GDR_COUNT_FLAG_* */
 #define GDR_COUNT_MAX_TILE 2  /* largest per-tile instance count; > tile_capacity => keys were dropped: re-run */
+#define GDR_COUNT_READY 3     /* set to 1 after the other words */
 #define GDR_COUNT_FLAG_PREFILTERED 2 /* prefiltered != 0 but a Gaussian failed the near-plane test (the reference traps
                                         on the device here, auxiliary.h:154-158) */
 
