@@ -73,6 +73,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
 
 def _build_locked(verbose: bool, extra_flags) -> str:
     srcs = _sources()
+    extra_flags = tuple(extra_flags) + tuple(os.environ.get("GDR_NVCC_FLAGS", "").split())  # experiments (-D...)
 
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")

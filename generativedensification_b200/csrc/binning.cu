@@ -24,7 +24,10 @@ namespace gdr {
 
 namespace {
 
-constexpr int SORT_THREADS = 256;
+#ifndef GDR_SORT_THREADS
+#define GDR_SORT_THREADS 256
+#endif
+constexpr int SORT_THREADS = GDR_SORT_THREADS;
 constexpr int SORT_CHUNK = 4096;  // keys per shared-memory sort (32 KB)
 constexpr int BUCKET_BITS = 10;
 constexpr int BUCKETS = 1 << BUCKET_BITS;   // depth buckets of the per-tile bucket sort
@@ -89,7 +92,8 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
     __shared__ uint32_t s_cnt[BUCKETS];        // bucket histogram, then fill cursors
     __shared__ uint32_t s_start[BUCKETS + 1];  // exclusive scan of the histogram
     __shared__ uint32_t s_wsum[SORT_THREADS / 32];
-    __shared__ uint32_t s_misc[4];             // min depth bits, max depth bits, largest bucket, stream base
+    __shared__ uint32_t s_misc[4];             // min depth bits, max depth bits, largest bucket
+    __shared__ uint32_t s_alloc[2];            // the tile's stream range: first record, records that fit
     pdl_wait();  // launched as a programmatic dependent of the projection kernel
     const int v = blockIdx.y;
     const float4* __restrict__ records =
@@ -98,32 +102,47 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
     float4* __restrict__ stream = stream0 + (size_t)v * capacity * RQ;
     const int tile = blockIdx.x;
     const uint32_t n_binned = min(img.tile_count[(size_t)tile * COUNT_STRIDE], tile_cap);  // claims beyond the segment were not stored
-    if (threadIdx.x == 0) {
-        // the tile's range of the stream, and its place in the blend kernels' heaviest-first order
-        uint32_t base = 0, n_fit = 0;
-        if (n_binned) {
-            base = atomicAdd(&img.header[HDR_CURSOR], n_binned);
+    if (n_binned == 0) {  // an empty tile: no stream range, last in the blend kernels' order
+        if (threadIdx.x == 0) {
+            img.tile_range[tile] = make_uint2(0u, 0u);
+            img.order[atomicAdd(&img.header[HDR_BUCKET0], 1u)] = (uint32_t)tile;
+        }
+        return;
+    }
+    // The tile's range of the stream comes from a global cursor.  Thread 0 issues the claim here and only looks at the
+    // answer when the sorted keys are ready (allocate() below): the atomic's round trip overlaps the sort.
+    uint32_t claimed = 0;
+    if (threadIdx.x == 0) claimed = atomicAdd(&img.header[HDR_CURSOR], n_binned);
+    auto allocate = [&]() {  // thread 0 publishes (base, records that fit) in s_misc[3], s_misc[2]; callers synchronise
+        if (threadIdx.x == 0) {
+            uint32_t base = claimed, n_fit = 0;
             if ((int64_t)base < capacity) n_fit = (uint32_t)min((int64_t)n_binned, capacity - (int64_t)base);
             else base = 0;
             if (n_fit < n_binned) atomicOr(&img.header[HDR_SORT_FLAGS], HDR_FLAG_STREAM_OVERFLOW);  // the host re-runs
+            img.tile_range[tile] = make_uint2(base, base + n_fit);
+            s_alloc[0] = base;
+            s_alloc[1] = n_fit;
         }
-        img.tile_range[tile] = make_uint2(base, base + n_fit);
-        const int bucket = n_fit ? 32 - __clz(n_fit) : 0;
-        img.order[(size_t)bucket * T + atomicAdd(&img.header[HDR_BUCKET0 + bucket], 1u)] = (uint32_t)tile;
-        s_misc[3] = base;
-        s_misc[2] = n_fit;
-    }
-    if (n_binned == 0) return;
-    __syncthreads();
-    const int64_t b = (int64_t)s_misc[3];
-    const int n = (int)s_misc[2];
-    __syncthreads();  // s_misc is reused below
-    if (n == 0) return;
+    };
+    const int n = (int)n_binned;
     uint64_t* seg = keys0 + (size_t)v * keys_stride + (size_t)tile * tile_cap;
-    // second key buffer of the long-list paths: the tile's own (not yet written) range of the record stream --
-    // n * RQ * 16 bytes, of which n * 8 are used; the gather below overwrites it after the sorted keys are back in `seg`
-    uint64_t* alt = reinterpret_cast<uint64_t*>(stream + (size_t)b * RQ);
     const uint64_t* sorted;  // where the sorted keys end up (shared memory or `seg`)
+    uint64_t* alt = nullptr;
+    if (n > BUCKET_MAX) {
+        // second key buffer of the long-list paths: the tile's own (not yet written) range of the record stream --
+        // RQ * 16 bytes per record, of which 8 are used; the gather below overwrites it after the sorted keys are back
+        // in `seg`.  These paths need the range first.
+        allocate();
+        __syncthreads();
+        if ((int)s_alloc[1] < n) {  // the stream is too small for this tile (the host re-runs the render): nothing to sort into
+            if (threadIdx.x == 0) {
+                img.tile_range[tile] = make_uint2(0u, 0u);
+                img.order[atomicAdd(&img.header[HDR_BUCKET0], 1u)] = (uint32_t)tile;
+            }
+            return;
+        }
+        alt = reinterpret_cast<uint64_t*>(stream + (size_t)s_alloc[0] * RQ);
+    }
 
     // ---- long lists (dense scenes: 2M Gaussians at 1600^2 give ~5000 instances per covered tile) ----
     // The same monotone depth-bucket sort, with the grouped copy and the result in global memory (both L2-resident
@@ -342,8 +361,17 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
     }
 
     // gather the Gaussians' records into the tile's contiguous, depth-ordered stream
-    float4* out = stream + (size_t)b * RQ;
-    for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+    if (alt == nullptr) {
+        allocate();
+        __syncthreads();
+    }
+    const int n_fit = (int)s_alloc[1];
+    if (threadIdx.x == 0) {  // the tile's place in the blend kernels' heaviest-first order
+        const int bucket = n_fit ? 32 - __clz(n_fit) : 0;
+        img.order[(size_t)bucket * T + atomicAdd(&img.header[HDR_BUCKET0 + bucket], 1u)] = (uint32_t)tile;
+    }
+    float4* out = stream + (size_t)s_alloc[0] * RQ;
+    for (int i = threadIdx.x; i < n_fit; i += SORT_THREADS) {
         const uint32_t id = (uint32_t)(sorted[i] & 0xffffffffu);
         const float4* src4 = records + (size_t)id * RQ;
         float4 w[RQ];

@@ -31,7 +31,10 @@ struct __align__(16) EmitRec {
 };
 static_assert(sizeof(EmitRec) == 64, "EmitRec must be 64 bytes");
 
-constexpr int EMIT_DEPTH = 8;  // 32-pair windows whose slot claims are in flight together
+#ifndef GDR_EMIT_DEPTH
+#define GDR_EMIT_DEPTH 8
+#endif
+constexpr int EMIT_DEPTH = GDR_EMIT_DEPTH;  // 32-pair windows whose slot claims are in flight together
 
 struct EmitTarget {
     uint32_t* tile_count;  // [T * COUNT_STRIDE] of this view
