@@ -230,7 +230,8 @@ int render_impl(const char* who, const gdr::Views& vw, int P, int W, int H, cons
     }
     {
         StageTimer t(GDR_STAGE_BLEND_FWD, s);
-        GDR_CUDA(gdr::launch_blend_forward(W, H, img, strm, capacity, out_color, out_depth, out_alpha, vw, s),
+        GDR_CUDA(gdr::launch_blend_forward(W, H, img, strm, capacity, out_color, out_depth, out_alpha, vw,
+                                           (flags & GDR_FLAG_FUSED_EPILOGUE) ? 1 : 0, s),
                  "blend_forward");
     }
     return GDR_OK;

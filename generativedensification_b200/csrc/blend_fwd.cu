@@ -42,7 +42,7 @@ constexpr int STAGES = 3;   // per-warp ring depth (two chunks in flight behind 
 __global__ void __launch_bounds__(BLEND_THREADS)
 blend_forward_kernel(int W, int H, int gx, int T, ImageState img0, const Splat* __restrict__ stream0, int64_t capacity,
                      float* __restrict__ out_color0, float* __restrict__ out_depth0, float* __restrict__ out_alpha0,
-                     const Views vw) {
+                     const Views vw, const int hwc_clamp) {
     __shared__ __align__(128) Splat buf[WARPS][STAGES][WCHUNK];
     __shared__ __align__(8) uint64_t full[WARPS][STAGES];
 
@@ -181,34 +181,42 @@ blend_forward_kernel(int W, int H, int gx, int T, ImageState img0, const Splat* 
     float Ta, Tb, wa, wb;
     upk(T2, Ta, Tb);
     upk(weight, wa, wb);
-    if (inside_a) {
-        const size_t pid = (size_t)pya * W + px;
-        n_contrib[pid] = last_a;
-        out_color[pid] = C0a + Ta * bg0;
-        out_color[HW + pid] = C1a + Ta * bg1;
-        out_color[2 * HW + pid] = C2a + Ta * bg2;
-        out_alpha[pid] = wa;
-        out_depth[pid] = Da;
-    }
-    if (inside_b) {
-        const size_t pid = (size_t)pyb * W + px;
-        n_contrib[pid] = last_b;
-        out_color[pid] = C0b + Tb * bg0;
-        out_color[HW + pid] = C1b + Tb * bg1;
-        out_color[2 * HW + pid] = C2b + Tb * bg2;
-        out_alpha[pid] = wb;
-        out_depth[pid] = Db;
-    }
+    // hwc_clamp: the epilogue of Renderer.render_img (lightning/renderer.py:261-265) fused in -- the colour leaves
+    // clamped to [0, 1] in HWC layout, and the channels the clamp cut are remembered for the backward
+    auto write_pixel = [&](int py, float c0, float c1, float c2, float T, float w, float d, uint32_t last) {
+        const size_t pid = (size_t)py * W + px;
+        c0 += T * bg0;
+        c1 += T * bg1;
+        c2 += T * bg2;
+        if (hwc_clamp) {
+            const unsigned cut = (!(c0 >= 0.f && c0 <= 1.f) ? 1u : 0u) | (!(c1 >= 0.f && c1 <= 1.f) ? 2u : 0u) |
+                                 (!(c2 >= 0.f && c2 <= 1.f) ? 4u : 0u);
+            float* o = out_color + 3 * pid;  // NaN stays NaN, as with torch.clamp
+            o[0] = c0 < 0.f ? 0.f : (c0 > 1.f ? 1.f : c0);
+            o[1] = c1 < 0.f ? 0.f : (c1 > 1.f ? 1.f : c1);
+            o[2] = c2 < 0.f ? 0.f : (c2 > 1.f ? 1.f : c2);
+            last |= cut << NCONTRIB_CLAMP_SHIFT;
+        } else {
+            out_color[pid] = c0;
+            out_color[HW + pid] = c1;
+            out_color[2 * HW + pid] = c2;
+        }
+        n_contrib[pid] = last;
+        out_alpha[pid] = w;
+        out_depth[pid] = d;
+    };
+    if (inside_a) write_pixel(pya, C0a, C1a, C2a, Ta, wa, Da, last_a);
+    if (inside_b) write_pixel(pyb, C0b, C1b, C2b, Tb, wb, Db, last_b);
 }
 
 }  // namespace
 
 cudaError_t launch_blend_forward(int W, int H, ImageState img, const Splat* stream, int64_t capacity,
-                                 float* out_color, float* out_depth, float* out_alpha, const Views& vw,
+                                 float* out_color, float* out_depth, float* out_alpha, const Views& vw, int hwc_clamp,
                                  cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     return launch_dependent(blend_forward_kernel, dim3(gx * gy, max(1, vw.V)), dim3(BLEND_THREADS), 0, s, W, H, gx, gx * gy, img,
-                            stream, capacity, out_color, out_depth, out_alpha, vw);
+                            stream, capacity, out_color, out_depth, out_alpha, vw, hwc_clamp);
 }
 
 }  // namespace gdr

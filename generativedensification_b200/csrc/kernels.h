@@ -72,8 +72,9 @@ cudaError_t launch_tile_sort_surfel(int W, int H, const void* surfel_records, Im
                                     int64_t tile_cap, void* surfel_stream, int64_t capacity, cudaStream_t s);
 
 // blend_fwd.cu
+// hwc_clamp: write out_color as the clamped [H][W][3] image of Renderer.render_img (GDR_FLAG_FUSED_EPILOGUE)
 cudaError_t launch_blend_forward(int W, int H, ImageState img, const Splat* stream, int64_t capacity,
-                                 float* out_color, float* out_depth, float* out_alpha, const Views& vw,
+                                 float* out_color, float* out_depth, float* out_alpha, const Views& vw, int hwc_clamp,
                                  cudaStream_t s);
 
 // blend_bwd.cu: accum is [V][P][12] floats: (mean2D x,y,|x|,|y|), (conic a,b,c, opacity), (r,g,b, depth)

@@ -85,20 +85,66 @@ def sum_over_ranks(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-def gather_view_results(local: Dict[int, torch.Tensor], n_views: int, device) -> List[torch.Tensor]:
-    """Collect per-view scalar results (e.g. PSNR) rendered under view sharding back in view order."""
-    vals = torch.full((n_views,), float("nan"), dtype=torch.float32, device=device)
+def gather_view_results(local: Dict[int, torch.Tensor], n_views: int, device) -> torch.Tensor:
+    """Collect per-view scalar results (e.g. PSNR) rendered under view sharding back in view order: a float32
+    [n_views] tensor on every rank.  Ownership travels as an explicit count per view (a NaN result is a legitimate
+    value, not a "not mine" marker); every view must have been rendered by exactly one rank."""
+    vals = torch.zeros(n_views, dtype=torch.float32, device=device)
+    owned = torch.zeros(n_views, dtype=torch.float32, device=device)
     for i, v in local.items():
         vals[i] = float(v)
+        owned[i] = 1.0
     if world() > 1:
-        gathered = [torch.empty_like(vals) for _ in range(world())]
-        dist.all_gather(gathered, vals)
-        stacked = torch.stack(gathered)
-        vals = torch.nan_to_num(stacked, nan=0.0).sum(0)
-        seen = (~torch.isnan(stacked)).sum(0)
-        if int(seen.min()) != 1 or int(seen.max()) != 1:
-            raise RuntimeError("view sharding did not cover every view exactly once")
+        both = torch.stack([vals, owned])
+        gathered = [torch.empty_like(both) for _ in range(world())]
+        dist.all_gather(gathered, both)
+        stacked = torch.stack(gathered)                 # [world, 2, n_views]
+        owned = stacked[:, 1].sum(0)
+        mine = stacked[:, 1] > 0
+        vals = torch.where(mine, stacked[:, 0], torch.zeros_like(stacked[:, 0])).sum(0)
+    if int(owned.min()) != 1 or int(owned.max()) != 1:
+        raise RuntimeError("view sharding did not cover every view exactly once")
     return vals
+
+
+def broadcast_gaussians(gaussians: Dict[str, torch.Tensor], src: int = 0) -> Dict[str, torch.Tensor]:
+    """View sharding of ONE object (BASELINE configs[4]; lightning/network.py:827-838 renders all views of an object
+    from the same Gaussians): rank `src` holds the attributes, every rank ends up with a replica -- one NCCL broadcast
+    per attribute tensor over NVLink (2 M Gaussians x 92 B = 184 MB), issued once per object.  Tensors must already be
+    allocated with the right shapes on every rank (receivers may pass torch.empty)."""
+    if world() > 1:
+        for k in sorted(gaussians):
+            dist.broadcast(gaussians[k], src=src)
+    return gaussians
+
+
+def gather_views(local: Dict[int, torch.Tensor], n_views: int, device=None) -> List[torch.Tensor]:
+    """All-gather per-view tensors (e.g. rendered images) produced under view sharding (`rank::world`): returns the
+    list of all n_views tensors in view order on every rank.  Every view must be present on exactly one rank."""
+    if world() == 1:
+        return [local[i] for i in range(n_views)]
+    w, r = world(), dist.get_rank()
+    some = next(iter(local.values())) if local else None
+    if device is None:
+        device = some.device if some is not None else torch.device("cuda", torch.cuda.current_device())
+    shape = [torch.zeros(8, dtype=torch.int64, device=device)]
+    if some is not None:
+        shape[0][0] = some.dim()
+        shape[0][1:1 + some.dim()] = torch.tensor(list(some.shape), device=some.device)
+    shapes = [torch.empty_like(shape[0]) for _ in range(w)]
+    dist.all_gather(shapes, shape[0])
+    ref_shape = next(tuple(int(x) for x in s[1:1 + int(s[0])]) for s in shapes if int(s[0]) > 0)
+    out: List[torch.Tensor] = [None] * n_views  # type: ignore[list-item]
+    rounds = (n_views + w - 1) // w
+    for j in range(rounds):  # round j: rank q contributes view j * w + q
+        mine = j * w + r
+        send = local[mine].contiguous() if mine < n_views else torch.zeros(ref_shape, dtype=torch.float32, device=device)
+        recv = [torch.empty_like(send) for _ in range(w)]
+        dist.all_gather(recv, send)
+        for q in range(w):
+            if j * w + q < n_views:
+                out[j * w + q] = recv[q]
+    return out
 
 
 class HostFeeder:

@@ -76,7 +76,7 @@ class _ViewsState:
 
 
 def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                   raw_params: bool = False):
+                   raw_params: bool = False, fused_epilogue: bool = False):
     lib = _lib.load()
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -93,9 +93,10 @@ def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scal
     st.capacity, st.num_rendered = 0, [0] * V
     st.geom = st.img = st.stream_buf = None
     radii = torch.empty(V, P, dtype=torch.int32, device=device)
+    color_shape = (V, H, W, 3) if fused_epilogue else (V, 3, H, W)
     if P == 0:  # the reference returns its zero-filled images untouched (rasterize_points.cu:83)
         z = torch.zeros
-        return z(V, 3, H, W, **f32), radii, z(V, 1, H, W, **f32), z(V, 1, H, W, **f32), st
+        return z(*color_shape, **f32), radii, z(V, 1, H, W, **f32), z(V, 1, H, W, **f32), st
 
     with torch.cuda.device(device):
         means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp = (
@@ -108,9 +109,10 @@ def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scal
         flags = 0 if options["tile_cull"] else _lib.FLAG_NO_TILE_CULL
         if raw_params:
             flags |= _lib.FLAG_RAW_PARAMS
-        color = torch.empty(V, 3, H, W, **f32)
+        color = torch.empty(*color_shape, **f32)
         depth = torch.empty(V, 1, H, W, **f32)
         alpha = torch.empty(V, 1, H, W, **f32)
+        render_flags = flags | (_lib.FLAG_FUSED_EPILOGUE if fused_epilogue else 0)
         one_view = _lib.query_bytes
 
         def project(tile_capacity: int):
@@ -130,7 +132,7 @@ def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scal
             _lib.check(lib.gdr_views_forward_render(
                 V, P, W, H, cb.cams.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(), st.stream_buf.data_ptr(),
                 scratch.data_ptr(), tile_capacity, capacity, color.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
-                flags | (_lib.FLAG_RERUN if rerun else 0), sptr), "gdr_views_forward_render")
+                render_flags | (_lib.FLAG_RERUN if rerun else 0), sptr), "gdr_views_forward_render")
 
         key = (device.index, P, H, W, flags, "views", V)
         rows = drive_forward(key, mailbox, stream, project, render)  # ONE host wait per batch
@@ -141,7 +143,7 @@ def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scal
 
 
 def _backward_views(cb: CameraBatch, st: _ViewsState, saved, grad_color, grad_depth, grad_alpha, needs,
-                    raw_params: bool = False):
+                    raw_params: bool = False, fused_epilogue: bool = False):
     lib = _lib.load()
     colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, alpha = saved
     device = means3D.device
@@ -182,6 +184,8 @@ def _backward_views(cb: CameraBatch, st: _ViewsState, saved, grad_color, grad_de
         return out
     if raw_params:
         mask |= _lib.GRAD_RAW_PARAMS
+    if fused_epilogue:
+        mask |= _lib.GRAD_HWC_COLOR  # grad_color is the gradient of the clamped [V,H,W,3] image
     with torch.cuda.device(device):
         grad_color = _f32c(grad_color, device)
         grad_depth = None if grad_depth is None else _f32c(grad_depth, device)
@@ -201,11 +205,12 @@ def _backward_views(cb: CameraBatch, st: _ViewsState, saved, grad_color, grad_de
 class _RasterizeViews(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, cameras,
-                raw_params=False):
+                raw_params=False, fused_epilogue=False):
         color, radii, depth, alpha, st = _forward_views(cameras, means3D, sh, colors_precomp, opacities, scales,
-                                                        rotations, cov3Ds_precomp, raw_params)
+                                                        rotations, cov3Ds_precomp, raw_params, fused_epilogue)
         ctx.cameras = cameras
         ctx.raw_params = bool(raw_params)
+        ctx.fused_epilogue = bool(fused_epilogue)
         ctx.state = st
         ctx.num_rendered = st.num_rendered
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, alpha)
@@ -219,22 +224,27 @@ class _RasterizeViews(torch.autograd.Function):
         saved = ctx.saved_tensors
         means3D = saved[1]
         if grad_color is None:
-            grad_color = torch.zeros(cb.V, 3, cb.height, cb.width, dtype=torch.float32, device=means3D.device)
+            shape = (cb.V, cb.height, cb.width, 3) if ctx.fused_epilogue else (cb.V, 3, cb.height, cb.width)
+            grad_color = torch.zeros(*shape, dtype=torch.float32, device=means3D.device)
         g = _backward_views(cb, st, saved, grad_color, grad_depth, grad_alpha, tuple(ctx.needs_input_grad[:8]),
-                            ctx.raw_params)
+                            ctx.raw_params, ctx.fused_epilogue)
         return (g["means3D"], g["means2D"], g["sh"], g["colors"], g["opacity"], g["scales"], g["rot"], g["cov3D"],
-                None, None)
+                None, None, None)
 
 
 def rasterize_views(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                    cameras: CameraBatch, raw_params: bool = False):
+                    cameras: CameraBatch, raw_params: bool = False, fused_epilogue: bool = False):
     """Batched counterpart of rasterize_gaussians(); `cameras` replaces `raster_settings`.
 
     raw_params=True: `opacities` are logits, `scales` log-scales and `rotations` un-normalised
     quaternions; sigmoid / exp / normalise run inside the projection kernel (bit-identical to activating
-    with torch first) and the returned gradients are w.r.t. the raw parameters."""
+    with torch first) and the returned gradients are w.r.t. the raw parameters.
+
+    fused_epilogue=True: the first output is Renderer.render_img's image -- clamped to [0, 1], in
+    [V,H,W,3] layout -- written by the blend kernel itself (lightning/renderer.py:261-265); its autograd is that of
+    `color.clamp(0, 1).permute(0, 2, 3, 1)`."""
     return _RasterizeViews.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                                 cameras, raw_params)
+                                 cameras, raw_params, fused_epilogue)
 
 
 class MultiViewRasterizer(nn.Module):
@@ -249,7 +259,7 @@ class MultiViewRasterizer(nn.Module):
             CameraBatch.from_settings(list(raster_settings))
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None, raw_params: bool = False):
+                cov3D_precomp=None, raw_params: bool = False, fused_epilogue: bool = False):
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
             raise Exception('Please provide excatly one of either SHs or precomputed colors!')
         if ((scales is None or rotations is None) and cov3D_precomp is None) or \
@@ -258,28 +268,33 @@ class MultiViewRasterizer(nn.Module):
         e = torch.Tensor([])
         return rasterize_views(means3D, means2D, e if shs is None else shs, e if colors_precomp is None else colors_precomp,
                                opacities, e if scales is None else scales, e if rotations is None else rotations,
-                               e if cov3D_precomp is None else cov3D_precomp, self.cameras, raw_params)
+                               e if cov3D_precomp is None else cov3D_precomp, self.cameras, raw_params, fused_epilogue)
 
 
 def render_images(cameras, centers, shs, opacity, scales, rotations, screenspace_points: Optional[torch.Tensor] = None,
                   opacity_activation=torch.sigmoid, scaling_activation=torch.exp,
                   rotation_activation=torch.nn.functional.normalize, prex: str = "",
-                  fused_activations: bool = False) -> dict:
+                  fused_activations: bool = False, fused_epilogue: bool = True) -> dict:
     """Renderer.render_img (lightning/renderer.py:209-272) for V views at once: activations, rasterize,
     clamp and the HWC permutes, stacked over the views: image [V,H,W,3], depth [V,H,W,1], acc_map [V,H,W].
 
     fused_activations=True applies the reference's default activations (sigmoid / exp / normalize) inside
-    the projection kernel instead of three torch passes (and their autograd nodes); same bits out."""
+    the projection kernel instead of three torch passes (and their autograd nodes); same bits out.
+    fused_epilogue=True (the default) lets the blend kernel write the clamped HWC image directly instead of
+    `image.clamp(0, 1).permute(0, 2, 3, 1)` (a clamp pass plus a strided view every consumer has to gather
+    through); same bits out, same gradients."""
     rast = cameras if isinstance(cameras, MultiViewRasterizer) else MultiViewRasterizer(cameras)
     if screenspace_points is None:
         screenspace_points = torch.zeros(centers.shape[0], 4, dtype=centers.dtype, device=centers.device,
                                          requires_grad=True) + 0
     if fused_activations:
         image, radii, depth, alpha = rast(means3D=centers, means2D=screenspace_points, shs=shs, opacities=opacity,
-                                          scales=scales, rotations=rotations, raw_params=True)
+                                          scales=scales, rotations=rotations, raw_params=True,
+                                          fused_epilogue=fused_epilogue)
     else:
         image, radii, depth, alpha = rast(means3D=centers, means2D=screenspace_points, shs=shs,
                                           opacities=opacity_activation(opacity), scales=scaling_activation(scales),
-                                          rotations=rotation_activation(rotations))
-    return {f"image{prex}": image.clamp(0, 1).permute(0, 2, 3, 1), f"depth{prex}": depth.permute(0, 2, 3, 1),
-            f"acc_map{prex}": alpha.squeeze(1)}
+                                          rotations=rotation_activation(rotations), fused_epilogue=fused_epilogue)
+    if not fused_epilogue:
+        image = image.clamp(0, 1).permute(0, 2, 3, 1)
+    return {f"image{prex}": image, f"depth{prex}": depth.permute(0, 2, 3, 1), f"acc_map{prex}": alpha.squeeze(1)}

@@ -81,6 +81,10 @@ extern "C" {
                                   w.r.t. the RAW parameters (through sigmoid / exp / normalise); `scales` and `rotations`
                                   passed to the backward are the raw ones */
 
+#define GDR_GRAD_HWC_COLOR 64   /* the forward ran with GDR_FLAG_FUSED_EPILOGUE: dL_dout_color is [H][W][3] (the gradient of
+                                  the clamped image); no gradient flows through a channel the clamp cut, as with
+                                  torch.clamp */
+
 /* flags for gdr_forward_project / gdr_forward_render (must be identical in both calls of a frame) */
 #define GDR_FLAG_NO_TILE_CULL 1 /* bin every tile of the reference's 3-sigma rectangle, exactly like the reference.
                                    Default (0): drop (Gaussian, tile) pairs that provably cannot reach
@@ -91,7 +95,11 @@ extern "C" {
                                    the projection kernel with torch's exact roundings.  gdr_forward_project only. */
 #define GDR_FLAG_RERUN 4        /* gdr_forward_render only: this render repeats an earlier one of the same projection
                                    (larger capacity); resets the stream cursor and the tile order lists first */
-#define GDR_FLAG_FUSED_EPILOGUE 8 /* gdr_views_forward_render only: see that function */
+#define GDR_FLAG_FUSED_EPILOGUE 8 /* gdr_forward_render / gdr_views_forward_render: fuse the epilogue of Renderer.render_img
+                                   (lightning/renderer.py:261-269) into the blend -- out_color is written as the image
+                                   clamped to [0, 1] in [H][W][3] layout ([V][H][W][3] for a batch); out_depth / out_alpha
+                                   are unchanged (their HW1 / HW forms are views).  The matching backward takes the
+                                   gradient w.r.t. that image: pass GDR_GRAD_HWC_COLOR in grad_mask */
 
 /* counts_host: 4 int32 per view in PINNED host memory that the device can address (cudaHostAlloc / cudaHostRegister,
  * unified addressing).  The projection kernel's last CTA stores words 0..2 and then word 3 = 1 with release / system

@@ -20,3 +20,13 @@ def device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """Say whether the unmodified compiled reference (oracle/_ref) took part in this run: its parity tests skip
+    without it (GDR_REQUIRE_REF=1 turns those skips into failures)."""
+    from oracle import ref_api
+
+    skipped = [r for r in terminalreporter.stats.get("skipped", []) if "oracle/_ref" in str(getattr(r, "longrepr", ""))]
+    state = "present" if ref_api.available() else "ABSENT"
+    terminalreporter.write_line(f"reference parity: oracle/_ref {state}; {len(skipped)} reference-parity test(s) skipped")

@@ -82,8 +82,7 @@ def test_golden_backward(name, device):
     checked = 0
     for k in sorted(g):
         if k.startswith("grad_") and g[k].size:
-            e_inf, _ = U.grad_errors(o[k], g[k])
-            assert e_inf <= GRAD_TOL, (k, e_inf)
+            U.assert_grad_close(o[k], g[k], k)  # norm-relative AND per-element relative (tests/util.py)
             checked += 1
     assert checked >= 5
 
@@ -259,8 +258,8 @@ def test_means2d_only_fast_path_matches_full_backward(device):
         return m2.grad
 
     g_fast, g_full = run(False), run(True)
-    e_inf, _ = U.grad_errors(g_fast.cpu().numpy(), g_full.cpu().numpy())
-    assert e_inf <= 1e-5  # same arithmetic per pair; only the float-atomic order differs
+    e_inf, rel = U.grad_errors(g_fast.cpu().numpy(), g_full.cpu().numpy())
+    assert e_inf <= 1e-5 and rel <= 1e-3  # same arithmetic per pair; only the float-atomic order differs
     assert (g_fast[:, 2:] >= 0).all()
 
 
@@ -317,7 +316,14 @@ def test_caller_pattern_of_the_reference_renderer(device):
 
 
 def _have_ref():
+    """oracle/_ref is built from /root/reference by __graft_entry__.build() and travels to the GPU box.  Without it the
+    reference-parity tests skip -- or, with GDR_REQUIRE_REF=1, fail, so that a green run cannot silently mean that no
+    comparison with the unmodified reference took place."""
+    import os
+
     from oracle import ref_api
+    if not ref_api.available() and os.environ.get("GDR_REQUIRE_REF") == "1":
+        return True  # run the tests: they fail loudly in ref_api.load()
     return ref_api.available()
 
 
@@ -352,8 +358,7 @@ def test_full_size_vs_compiled_reference(P, V, backward, device):
         if backward:
             for k in sorted(r):
                 if k.startswith("grad_") and r[k].size:
-                    e_inf, _ = U.grad_errors(o[k], r[k])
-                    assert e_inf <= GRAD_TOL, (k, e_inf)
+                    U.assert_grad_close(o[k], r[k], k)
 
 
 @pytest.mark.skipif(not _have_ref(), reason="oracle/_ref (compiled reference) not present")
@@ -400,8 +405,7 @@ def test_config5_stress_vs_compiled_reference(device):
     assert U.max_abs(o["color"], r["color"]) <= 2e-6
     for k in sorted(r):
         if k.startswith("grad_") and r[k].size:
-            e_inf, _ = U.grad_errors(o[k], r[k])
-            assert e_inf <= GRAD_TOL, (k, e_inf)
+            U.assert_grad_close(o[k], r[k], k)
 
 
 @pytest.mark.skipif(not _have_ref(), reason="oracle/_ref (compiled reference) not present")
@@ -436,8 +440,7 @@ def test_config4_densify_select_vs_reference(device):
     ref_loss = ((torch.stack(images) - torch.stack(targets)) ** 2).mean()
     (ref_grad,) = torch.autograd.grad(ref_loss, screenspace)
     assert abs(float(loss) - float(ref_loss.detach())) <= 1e-6
-    e_inf, _ = U.grad_errors(grad.cpu().numpy(), ref_grad.cpu().numpy())
-    assert e_inf <= GRAD_TOL
+    U.assert_grad_close(grad, ref_grad, "screenspace grad")
     ref_sel = densify.select_top_k(ref_grad, K)
     overlap = int((sel & ref_sel).sum()) / K
     assert overlap >= 0.999  # only near-ties at the K-th value may differ (float-atomic summation order)

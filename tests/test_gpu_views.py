@@ -161,3 +161,39 @@ def test_fused_activations_match_torch_activations(device):
     for k in raw:
         err, _ = U.grad_errors(outs[True][1][k].cpu().numpy(), outs[False][1][k].cpu().numpy())
         assert err <= 1e-4, (k, err)
+
+
+def test_fused_epilogue_matches_clamp_and_permute(device):
+    """the blend kernel writing Renderer.render_img's clamped HWC image (lightning/renderer.py:261-265)
+    == `color.clamp(0, 1).permute(...)` after the fact: same bits forward, and the same gradients -- including NO
+    gradient through the channels the clamp cut (bright SH colours push many pixels above 1, a dark background
+    colour and negative DC terms push others below 0)."""
+    from generativedensification_b200.views import render_images
+
+    V, W, H, P = 3, 112, 80, 5000
+    st = _settings(V, W, H, device)
+    st = [s._replace(bg=torch.tensor([0.2, 1.0, 0.0], device=device)) for s in st]
+    gen = torch.Generator().manual_seed(41)
+    shs = torch.randn(P, 4, 3, generator=gen) * 2.5  # colours far outside [0, 1] on both sides
+    raw = dict(centers=(torch.rand(P, 3, generator=gen) - 0.5), shs=shs,
+               opacity=torch.randn(P, 1, generator=gen) * 1.5 + 0.5, scales=torch.randn(P, 3, generator=gen) * 0.3 - 3.6,
+               rotations=torch.randn(P, 4, generator=gen))
+    outs = {}
+    for fused in (False, True):
+        leaves = {k: v.to(device).clone().requires_grad_(True) for k, v in raw.items()}
+        o = render_images(st, leaves["centers"], leaves["shs"], leaves["opacity"], leaves["scales"],
+                          leaves["rotations"], fused_epilogue=fused)
+        assert o["image"].shape == (V, H, W, 3) and o["depth"].shape == (V, H, W, 1) and o["acc_map"].shape == (V, H, W)
+        g = torch.Generator().manual_seed(42)
+        loss = sum((o[k] * torch.randn(o[k].shape, generator=g).to(device)).sum() for k in ("image", "depth", "acc_map"))
+        grads = torch.autograd.grad(loss, list(leaves.values()))
+        outs[fused] = (o, dict(zip(leaves, grads)))
+    img = outs[True][0]["image"]
+    assert outs[True][0]["image"].is_contiguous()
+    cut = ((img == 0) | (img == 1)).float().mean()
+    assert 0.05 < float(cut) < 0.95  # the clamp is active on a good part of the image, but not everywhere
+    for k in ("image", "depth", "acc_map"):
+        assert torch.equal(outs[True][0][k], outs[False][0][k]), k
+    for k in raw:
+        err, _ = U.grad_errors(outs[True][1][k].cpu().numpy(), outs[False][1][k].cpu().numpy())
+        assert err <= 1e-4, (k, err)  # same arithmetic per pair; only the float-atomic order differs

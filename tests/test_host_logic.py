@@ -43,15 +43,20 @@ def _worker(rank, world, port, q):
     dev = torch.device("cpu")
     mine = shard.shard_indices(8, r, w)
     # each rank "renders" its views; the per-view scalar is just a function of the view index
-    local = {i: torch.tensor(float(i * i)) for i in mine}
+    local = {i: torch.tensor(float("nan") if i == 5 else float(i * i)) for i in mine}  # a NaN result is a value
     vals = shard.gather_view_results(local, 8, dev)
+    # view sharding of one object: Gaussians broadcast from rank 0, per-view images gathered back in view order
+    gs = {"means3D": torch.arange(12.0).reshape(4, 3) if r == 0 else torch.empty(4, 3),
+          "opacities": torch.full((4, 1), 0.5) if r == 0 else torch.empty(4, 1)}
+    shard.broadcast_gaussians(gs, src=0)
+    images = shard.gather_views({i: torch.full((2, 3), float(i)) + gs["means3D"][0, :3] for i in mine}, 8, dev)
     g = shard.gather_scalars([float(r), float(len(mine))], dev)
     grad = torch.full((5, 4), float(r + 1))
     shard.sum_over_ranks(grad)
     t = shard.max_over_ranks(10.0 + r, dev)
     shard.barrier()
-    if r == 0:
-        q.put((vals.tolist(), g.tolist(), grad[0].tolist(), t))
+    if r == 1:  # the non-source rank reports what it received
+        q.put((vals.tolist(), g.tolist(), grad[0].tolist(), t, gs["means3D"].tolist(), [im.tolist() for im in images]))
     dist.destroy_process_group()
 
 
@@ -62,11 +67,14 @@ def test_two_rank_gloo_sharding():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    vals, g, grad0, t = q.get(timeout=120)
+    vals, g, grad0, t, means, images = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert vals == [float(i * i) for i in range(8)]
+    assert math.isnan(vals[5])
+    assert [v for i, v in enumerate(vals) if i != 5] == [float(i * i) for i in range(8) if i != 5]
+    assert means == torch.arange(12.0).reshape(4, 3).tolist()  # broadcast_gaussians
+    assert images == [(torch.full((2, 3), float(i)) + torch.tensor([0.0, 1.0, 2.0])).tolist() for i in range(8)]
     assert g == [[0.0, 4.0], [1.0, 4.0]]
     assert grad0 == [3.0, 3.0, 3.0, 3.0]       # 1 + 2: the [P,4] gradient sums across ranks
     assert t == 11.0

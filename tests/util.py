@@ -156,6 +156,36 @@ def grad_errors(ours, ref, floor=1e-6):
     return float(err_inf), float(rel)
 
 
+# Gradient tolerances (BASELINE.json north star: "1e-3 rel on gradients").  Per tensor:
+#   * norm-relative:  max |ours - ref| <= GRAD_TOL * max |ref|;
+#   * per element, for every element that is not small against the tensor (|ref| > max(1e-6, 1e-2 max |ref|)):
+#     |ours - ref| / |ref| <= GRAD_ELEM_TOL.
+# Both sides accumulate with float atomics in a run-dependent order, so two runs of the UNMODIFIED reference differ
+# from each other by a few 1e-4 norm-relative on the conditioning-sensitive tensors (tools/grad_rel_survey.py prints
+# that noise floor next to our error); elements below 1e-2 of the tensor's maximum are covered by the norm bound only.
+GRAD_TOL = 1e-3
+GRAD_ELEM_TOL = 2e-2
+GRAD_ELEM_FRAC = 1e-2
+
+
+def assert_grad_close(ours, ref, name="grad", tol=GRAD_TOL, elem_tol=GRAD_ELEM_TOL):
+    """Assert both bounds above; accepts numpy arrays or tensors."""
+    to_np = lambda t: t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
+    ours, ref = to_np(ours).astype(np.float64), to_np(ref).astype(np.float64)
+    assert ours.shape == ref.shape or ours.size == ref.size, (name, ours.shape, ref.shape)
+    ours = ours.reshape(ref.shape)
+    if ref.size == 0:
+        return 0.0, 0.0
+    scale = max(np.abs(ref).max(), 1e-30)
+    err = np.abs(ours - ref)
+    e_inf = float(err.max() / scale)
+    assert e_inf <= tol, (name, "norm-relative", e_inf)
+    big = np.abs(ref) > max(1e-6, GRAD_ELEM_FRAC * scale)
+    rel = float((err[big] / np.abs(ref)[big]).max()) if big.any() else 0.0
+    assert rel <= elem_tol, (name, "per-element relative", rel)
+    return e_inf, rel
+
+
 def psnr(a, b):
     mse = float(((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2).mean())
     return 99.0 if mse == 0 else -10.0 * np.log10(mse)
