@@ -157,22 +157,25 @@ def grad_errors(ours, ref, floor=1e-6):
 
 
 # Gradient tolerances (BASELINE.json north star: "1e-3 rel on gradients").  Per tensor:
-#   * norm-relative:  max |ours - ref| <= GRAD_TOL * max |ref|;
-#   * per element, for every element that is not small against the tensor (|ref| > max(1e-6, 1e-2 max |ref|)):
-#     |ours - ref| / |ref| <= GRAD_ELEM_TOL.
-# Both sides accumulate with float atomics in a run-dependent order, so two runs of the UNMODIFIED reference differ
-# from each other by a few 1e-4 norm-relative on the conditioning-sensitive tensors (tools/grad_rel_survey.py prints
-# that noise floor next to our error); elements below 1e-2 of the tensor's maximum are covered by the norm bound only.
+#   * norm-relative:  max |ours - ref| <= 1e-3 * max |ref|;
+#   * per element, for every element with |ref| > max(1e-6, 1e-3 * max |ref|):
+#         |ours - ref| <= 1e-3 * |ref| + 1e-6 * max |ref|
+#     (the allclose form: relative 1e-3, with an absolute term three decades below the selection threshold).
+# Both sides accumulate with float atomics in a run-dependent order: two runs of the UNMODIFIED reference differ from
+# each other by up to ~1e-4 per element at this threshold (tools/grad_rel_survey.py prints that noise floor next to our
+# error: worst 8.9e-4 on the golden scenes, 1.8e-4 at 200k Gaussians / 800x800).
 GRAD_TOL = 1e-3
-GRAD_ELEM_TOL = 2e-2
-GRAD_ELEM_FRAC = 1e-2
+GRAD_ELEM_RTOL = 1e-3
+GRAD_ELEM_ATOL = 1e-6  # times max |ref|
+GRAD_ELEM_FRAC = 1e-3
 
 
-def assert_grad_close(ours, ref, name="grad", tol=GRAD_TOL, elem_tol=GRAD_ELEM_TOL):
-    """Assert both bounds above; accepts numpy arrays or tensors."""
+def assert_grad_close(ours, ref, name="grad", tol=GRAD_TOL, elem_rtol=GRAD_ELEM_RTOL):
+    """Assert both bounds above; accepts numpy arrays or tensors.  Returns (norm-relative error, worst per-element
+    relative error over the selected elements)."""
     to_np = lambda t: t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
     ours, ref = to_np(ours).astype(np.float64), to_np(ref).astype(np.float64)
-    assert ours.shape == ref.shape or ours.size == ref.size, (name, ours.shape, ref.shape)
+    assert ours.size == ref.size, (name, ours.shape, ref.shape)
     ours = ours.reshape(ref.shape)
     if ref.size == 0:
         return 0.0, 0.0
@@ -182,7 +185,8 @@ def assert_grad_close(ours, ref, name="grad", tol=GRAD_TOL, elem_tol=GRAD_ELEM_T
     assert e_inf <= tol, (name, "norm-relative", e_inf)
     big = np.abs(ref) > max(1e-6, GRAD_ELEM_FRAC * scale)
     rel = float((err[big] / np.abs(ref)[big]).max()) if big.any() else 0.0
-    assert rel <= elem_tol, (name, "per-element relative", rel)
+    bad = err[big] > elem_rtol * np.abs(ref)[big] + GRAD_ELEM_ATOL * scale
+    assert not bad.any(), (name, "per-element relative", rel, int(bad.sum()))
     return e_inf, rel
 
 

@@ -97,12 +97,12 @@ def run_fused(g, cams_eval, cams_sel, targets, ev):
     from generativedensification_b200 import densify as D
     from generativedensification_b200.views import MultiViewRasterizer
 
-    def render(gs, cb):
+    def render(gs, cb):  # the blend kernel writes Renderer.render_img's clamped HWC image itself (fused epilogue)
         m2 = torch.zeros(gs["means3D"].shape[0], 4, device=gs["means3D"].device)
-        color, radii, depth, alpha = MultiViewRasterizer(cb)(
+        image, radii, depth, alpha = MultiViewRasterizer(cb)(
             means3D=gs["means3D"], means2D=m2, shs=gs["shs"], opacities=gs["opacities"], scales=gs["scales"],
-            rotations=gs["rotations"])
-        return color.clamp(0, 1).permute(0, 2, 3, 1), depth.permute(0, 2, 3, 1), alpha.squeeze(1)
+            rotations=gs["rotations"], fused_epilogue=True)
+        return image, depth.permute(0, 2, 3, 1), alpha.squeeze(1)
 
     ev[0].record()
     with torch.no_grad():
@@ -119,32 +119,26 @@ def run_fused(g, cams_eval, cams_sel, targets, ev):
     return imgs, imgs2, out["selected"]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--objects", type=int, default=8)
-    ap.add_argument("--res", type=int, default=800)
-    ap.add_argument("--warmup", type=int, default=1)
-    ap.add_argument("--arms", default="reference,ours-loop,ours-fused")
-    a = ap.parse_args()
-    rank, world, local_rank = shard.init_distributed()
+def run(objects, res, warmup, arms, rank, world, local_rank):
+    """Times the requested arms; returns {"workload", "n_gpus", "arms": {...}} (complete on rank 0)."""
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     import generativedensification_b200.rasterizer as ours
     from generativedensification_b200.views import CameraBatch
     from oracle import ref_api
 
-    cams = S.orbit_cameras(V_EVAL, a.res, a.res)
+    cams = S.orbit_cameras(V_EVAL, res, res)
     bg = torch.ones(3)
     settings_eval = [S.settings_for(c, bg, 1, device) for c in cams]
     settings_sel = settings_eval[:V_SEL]
     cb_eval = CameraBatch.from_settings(settings_eval)
     cb_sel = CameraBatch.from_settings(settings_sel)
     gen = torch.Generator().manual_seed(4242)
-    targets = torch.rand(V_SEL, a.res, a.res, 3, generator=gen).to(device)
+    targets = torch.rand(V_SEL, res, res, 3, generator=gen).to(device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    my_objects = shard.shard_indices(a.objects, rank, world)
+    my_objects = shard.shard_indices(objects, rank, world)
     results = {}
-    for arm in a.arms.split(","):
+    for arm in arms:
         if arm == "reference":
             if not ref_api.available():
                 results[arm] = {"unavailable": "oracle/_ref not built"}
@@ -159,7 +153,7 @@ def main():
             fn = lambda g, ev: run_fused(g, cb_eval, cb_sel, targets, ev)
         phases = [0.0] * 4
         total = 0.0
-        for it in range(a.warmup):
+        for it in range(warmup):
             fn(make_object(1238, device), [torch.cuda.Event(enable_timing=True) for _ in range(5)])
         torch.cuda.synchronize(device)
         shard.barrier()
@@ -174,14 +168,26 @@ def main():
             total += ev[0].elapsed_time(ev[4])
         shard.barrier()
         total_max = shard.max_over_ranks(total, device)
-        n_views = (2 * V_EVAL + V_SEL) * a.objects
+        n_views = (2 * V_EVAL + V_SEL) * objects
         results[arm] = {"views_per_s": n_views / (total_max * 1e-3), "ms_per_object": total / max(len(my_objects), 1),
                         "phase_ms_per_object": {k: round(v / max(len(my_objects), 1), 3) for k, v in
                                                 zip(("pass1_32v_fwd", "densify_4v_fwd_bwd_topk", "build_fine_set",
                                                      "pass2_32v_fwd"), phases)}}
+    return {"workload": f"BASELINE configs[3]: {objects} objects x (32 + 4 + 32) views, {res}x{res}, "
+                        f"P={P_COARSE}, K={K_NUM}, fine set 331 744", "n_gpus": world, "arms": results}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--objects", type=int, default=8)
+    ap.add_argument("--res", type=int, default=800)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--arms", default="reference,ours-loop,ours-fused")
+    a = ap.parse_args()
+    rank, world, local_rank = shard.init_distributed()
+    out = run(a.objects, a.res, a.warmup, a.arms.split(","), rank, world, local_rank)
     if rank == 0:
-        print(json.dumps({"workload": f"BASELINE configs[3]: {a.objects} objects x (32 + 4 + 32) views, {a.res}x{a.res}, "
-                                      f"P={P_COARSE}, K={K_NUM}, fine set 331 744", "n_gpus": world, "arms": results}))
+        print(json.dumps(out))
     shard.shutdown()
 
 
