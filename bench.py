@@ -394,6 +394,8 @@ def main():
             e1.record()
             torch.cuda.synchronize(device)
             t_bcast = e0.elapsed_time(e1)
+            if rank != 0:
+                g = {k: v.cpu() for k, v in gd.items()}  # the host copy the end-to-end arm feeds from
         else:
             gd = {k: v.to(device) for k, v in g.items()}
         return g, gd, [cams[i] for i in my_views], up, t_bcast

@@ -37,15 +37,18 @@ SIGNATURES = {
     "gdr_image_state_bytes": (_i, [_i, _i, _pi64]),
     "gdr_splat_stream_bytes": (_i, [_i64, _pi64]),
     "gdr_sort_scratch_bytes": (_i, [_i, _i, _i64, _pi64]),
+    "gdr_sort_scratch_exact_bytes": (_i, [_i64, _pi64]),
     "gdr_backward_scratch_bytes": (_i, [_i, _pi64]),
+    "gdr_tile_offsets": (_i, [_i, _i, _i, _vp, _vp, _vp]),
     "gdr_forward_project": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _i,
-                                 _vp, _vp, _vp, _vp, _i64, _vp, _i, _vp]),
-    "gdr_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _vp]),
+                                 _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp]),
+    "gdr_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
     "gdr_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp,
                           _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gdr_views_forward_project": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _vp, _vp,
-                                       _vp, _vp, _i64, _vp, _i, _vp]),
-    "gdr_views_forward_render": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _vp]),
+                                       _vp, _vp, _i64, _vp, _vp, _i, _vp]),
+    "gdr_views_forward_render": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i,
+                                      _vp]),
     "gdr_views_backward": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
                                 _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gdr_mse_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
@@ -57,8 +60,9 @@ SIGNATURES = {
     "gdr_surfel_aux_bytes": (_i, [_i, _i, _pi64]),
     "gdr_surfel_backward_scratch_bytes": (_i, [_i, _pi64]),
     "gdr_surfel_forward_project": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp,
-                                        _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
-    "gdr_surfel_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _vp]),
+                                        _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "gdr_surfel_forward_render": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i,
+                                       _vp]),
     "gdr_surfel_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp]),

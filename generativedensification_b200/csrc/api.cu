@@ -96,6 +96,13 @@ int gdr_sort_scratch_bytes(int W, int H, int64_t tile_capacity, int64_t* bytes) 
     return GDR_OK;
 }
 
+int gdr_sort_scratch_exact_bytes(int64_t num_keys, int64_t* bytes) {
+    if (num_keys <= 0 || (num_keys & 31) || !bytes)
+        return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_sort_scratch_exact_bytes: num_keys must be a positive multiple of 32");
+    *bytes = (int64_t)gdr::key_bytes_per_view(1, 1, num_keys, true);
+    return GDR_OK;
+}
+
 int gdr_backward_scratch_bytes(int P, int64_t* bytes) {
     if (P < 0 || !bytes) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_backward_scratch_bytes: bad arguments");
     *bytes = (int64_t)sizeof(float) * 12 * P + 256;
@@ -137,7 +144,7 @@ gdr::Views batched_views(int V, int P, int W, int H, const gdr_camera* cams) {
 
 int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, int M, int W, int H, const GaussianInputs& g,
                  int prefiltered, int32_t* radii, void* geom_state, void* image_state, void* sort_scratch,
-                 int64_t tile_capacity, int32_t* counts_host, int flags, cudaStream_t s) {
+                 int64_t tile_capacity, const uint32_t* tile_offsets, int32_t* counts_host, int flags, cudaStream_t s) {
     if (P < 0 || W <= 0 || H <= 0 || vw.V <= 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
     if (P >= (1 << gdr::STREAM_REGION_SHIFT))
         return fail(GDR_ERR_UNSUPPORTED, "%s: at most 2^28 - 1 Gaussians per call", who);
@@ -183,8 +190,9 @@ int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, in
         a.geom = gdr::GeomState::carve(geom_state, (size_t)P);
         a.img = img;
         a.keys = (uint64_t*)sort_scratch;
-        a.keys_stride = gdr::sort_scratch_bytes(W, H, tile_capacity) / sizeof(uint64_t);
+        a.keys_stride = gdr::key_bytes_per_view(W, H, tile_capacity, tile_offsets != nullptr) / sizeof(uint64_t);
         a.tile_cap = (uint32_t)tile_capacity;
+        a.tile_base = tile_offsets;
         a.counts_host = counts_host;  // written by the kernel's last CTA: no copy node between it and tile_sort
         {
             StageTimer t(GDR_STAGE_PROJECT, s);
@@ -200,8 +208,8 @@ int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, in
 }
 
 int render_impl(const char* who, const gdr::Views& vw, int P, int W, int H, const void* geom_state, void* image_state,
-                void* splat_stream, void* sort_scratch, int64_t tile_capacity, int64_t capacity, float* out_color,
-                float* out_depth, float* out_alpha, int flags, cudaStream_t s) {
+                void* splat_stream, void* sort_scratch, int64_t tile_capacity, const uint32_t* tile_offsets,
+                int64_t capacity, float* out_color, float* out_depth, float* out_alpha, int flags, cudaStream_t s) {
     if (P < 0 || W <= 0 || H <= 0 || capacity < 0 || vw.V <= 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
     if (!image_state || !vw.bg || !out_color || !out_depth || !out_alpha)
         return fail(GDR_ERR_INVALID_ARGUMENT, "%s: a required pointer is NULL", who);
@@ -224,8 +232,8 @@ int render_impl(const char* who, const gdr::Views& vw, int P, int W, int H, cons
         gdr::GeomState geom = gdr::GeomState::carve(const_cast<void*>(geom_state), (size_t)(P > 0 ? P : 0));
         StageTimer t(GDR_STAGE_TILE_SORT, s);
         // runs for P == 0 too: it files every (empty) tile in the order lists the blend kernel walks
-        GDR_CUDA(gdr::launch_tile_sort(W, H, geom, img, (uint64_t*)sort_scratch, P > 0 ? tile_capacity : 32, strm, capacity, vw,
-                                       s),
+        GDR_CUDA(gdr::launch_tile_sort(W, H, geom, img, (uint64_t*)sort_scratch, P > 0 ? tile_capacity : 32,
+                                       P > 0 ? tile_offsets : nullptr, strm, capacity, vw, s),
                  "tile_sort");
     }
     {
@@ -293,19 +301,33 @@ int gdr_forward_project(int P, int sh_degree, int M, int W, int H, const float* 
                         float scale_modifier, const float* rotations, const float* cov3D_precomp,
                         const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
                         float tan_fovy, int prefiltered, int32_t* radii, void* geom_state, void* image_state,
-                        void* sort_scratch, int64_t tile_capacity, int32_t* counts_host, int flags, void* stream) {
+                        void* sort_scratch, int64_t tile_capacity, const uint32_t* tile_offsets, int32_t* counts_host,
+                        int flags, void* stream) {
     const GaussianInputs g = {means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, scale_modifier};
     return project_impl("gdr_forward_project", single_view(P, W, H, viewmatrix, projmatrix, campos, nullptr, tan_fovx, tan_fovy),
                         P, sh_degree, M, W, H, g, prefiltered, radii, geom_state, image_state, sort_scratch, tile_capacity,
-                        counts_host, flags, (cudaStream_t)stream);
+                        tile_offsets, counts_host, flags, (cudaStream_t)stream);
 }
 
 int gdr_forward_render(int P, int W, int H, const float* bg, const void* geom_state, void* image_state,
-                       void* splat_stream, void* sort_scratch, int64_t tile_capacity, int64_t capacity,
-                       float* out_color, float* out_depth, float* out_alpha, int flags, void* stream) {
+                       void* splat_stream, void* sort_scratch, int64_t tile_capacity, const uint32_t* tile_offsets,
+                       int64_t capacity, float* out_color, float* out_depth, float* out_alpha, int flags, void* stream) {
     return render_impl("gdr_forward_render", single_view(P, W, H, nullptr, nullptr, nullptr, bg, 0.f, 0.f), P, W, H,
-                       geom_state, image_state, splat_stream, sort_scratch, tile_capacity, capacity, out_color, out_depth,
-                       out_alpha, flags, (cudaStream_t)stream);
+                       geom_state, image_state, splat_stream, sort_scratch, tile_capacity, tile_offsets, capacity,
+                       out_color, out_depth, out_alpha, flags, (cudaStream_t)stream);
+}
+
+int gdr_tile_offsets(int V, int W, int H, const void* image_states, uint32_t* tile_offsets, void* stream) {
+    if (V <= 0 || W <= 0 || H <= 0 || !image_states || !tile_offsets)
+        return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_tile_offsets: bad arguments");
+    gdr::Views vw;
+    memset(&vw, 0, sizeof(vw));
+    vw.V = V;
+    vw.img_stride = V > 1 ? gdr::ImageState::bytes(W, H) : 0;
+    GDR_CUDA(gdr::launch_tile_offsets(W, H, gdr::ImageState::carve(const_cast<void*>(image_states), W, H), tile_offsets, vw,
+                                      (cudaStream_t)stream),
+             "tile_offsets");
+    return GDR_OK;
 }
 
 int gdr_backward(int P, int sh_degree, int M, int W, int H, const float* bg, const float* means3D, const float* shs,
@@ -330,23 +352,23 @@ int gdr_views_forward_project(int V, int P, int sh_degree, int M, int W, int H, 
                               const float* colors_precomp, const float* opacities, const float* scales,
                               float scale_modifier, const float* rotations, const float* cov3D_precomp,
                               const gdr_camera* cameras, int prefiltered, int32_t* radii, void* geom_states,
-                              void* image_states, void* sort_scratch, int64_t tile_capacity, int32_t* counts_host,
-                              int flags, void* stream) {
+                              void* image_states, void* sort_scratch, int64_t tile_capacity,
+                              const uint32_t* tile_offsets, int32_t* counts_host, int flags, void* stream) {
     if (V <= 0 || !cameras) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_views_forward_project: bad V or cameras is NULL");
     const GaussianInputs g = {means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, scale_modifier};
     return project_impl("gdr_views_forward_project", batched_views(V, P, W, H, cameras), P, sh_degree, M, W, H, g,
-                        prefiltered, radii, geom_states, image_states, sort_scratch, tile_capacity, counts_host, flags,
-                        (cudaStream_t)stream);
+                        prefiltered, radii, geom_states, image_states, sort_scratch, tile_capacity, tile_offsets,
+                        counts_host, flags, (cudaStream_t)stream);
 }
 
 int gdr_views_forward_render(int V, int P, int W, int H, const gdr_camera* cameras, const void* geom_states,
                              void* image_states, void* splat_streams, void* sort_scratch, int64_t tile_capacity,
-                             int64_t capacity_per_view, float* out_color, float* out_depth, float* out_alpha, int flags,
-                             void* stream) {
+                             const uint32_t* tile_offsets, int64_t capacity_per_view, float* out_color, float* out_depth,
+                             float* out_alpha, int flags, void* stream) {
     if (V <= 0 || !cameras) return fail(GDR_ERR_INVALID_ARGUMENT, "gdr_views_forward_render: bad V or cameras is NULL");
     return render_impl("gdr_views_forward_render", batched_views(V, P, W, H, cameras), P, W, H, geom_states, image_states,
-                       splat_streams, sort_scratch, tile_capacity, capacity_per_view, out_color, out_depth, out_alpha,
-                       flags, (cudaStream_t)stream);
+                       splat_streams, sort_scratch, tile_capacity, tile_offsets, capacity_per_view, out_color, out_depth,
+                       out_alpha, flags, (cudaStream_t)stream);
 }
 
 int gdr_views_backward(int V, int P, int sh_degree, int M, int W, int H, const float* means3D, const float* shs,
@@ -449,8 +471,8 @@ int gdr_surfel_forward_project(int P, int sh_degree, int M, int W, int H, const 
                                int scale_stride, float scale_modifier, const float* rotations,
                                const float* transmat_precomp, const float* viewmatrix, const float* projmatrix,
                                const float* campos, int32_t* radii, void* geom_state, void* surfel_state,
-                               void* image_state, void* sort_scratch, int64_t tile_capacity, int32_t* counts_host,
-                               void* stream) {
+                               void* image_state, void* sort_scratch, int64_t tile_capacity,
+                               const uint32_t* tile_offsets, int32_t* counts_host, void* stream) {
     const char* who = "gdr_surfel_forward_project";
     cudaStream_t s = (cudaStream_t)stream;
     if (P < 0 || W <= 0 || H <= 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
@@ -477,7 +499,8 @@ int gdr_surfel_forward_project(int P, int sh_degree, int M, int W, int H, const 
         GDR_CUDA(gdr::launch_surfel_project(P, sh_degree, M, W, H, means3D, shs, colors_precomp, opacities, scales,
                                             scale_stride, scale_modifier, rotations, transmat_precomp, viewmatrix,
                                             projmatrix, campos, radii, gdr::GeomState::carve(geom_state, (size_t)P),
-                                            surfel_state, img, (uint64_t*)sort_scratch, tile_capacity, counts_host, s),
+                                            surfel_state, img, (uint64_t*)sort_scratch, tile_capacity, tile_offsets,
+                                            counts_host, s),
                  "surfel_project");
     } else if (counts_host) {
         counts_host[0] = counts_host[1] = counts_host[2] = 0;
@@ -488,8 +511,8 @@ int gdr_surfel_forward_project(int P, int sh_degree, int M, int W, int H, const 
 
 int gdr_surfel_forward_render(int P, int W, int H, const float* bg, const void* geom_state, const void* surfel_state,
                               void* image_state, void* surfel_stream, void* sort_scratch, int64_t tile_capacity,
-                              int64_t capacity, float* out_color, float* out_allmap, void* surfel_aux, int flags,
-                              void* stream) {
+                              const uint32_t* tile_offsets, int64_t capacity, float* out_color, float* out_allmap,
+                              void* surfel_aux, int flags, void* stream) {
     const char* who = "gdr_surfel_forward_render";
     cudaStream_t s = (cudaStream_t)stream;
     if (P < 0 || W <= 0 || H <= 0 || capacity < 0) return fail(GDR_ERR_INVALID_ARGUMENT, "%s: bad sizes", who);
@@ -507,7 +530,8 @@ int gdr_surfel_forward_render(int P, int W, int H, const float* bg, const void* 
     {
         StageTimer t(GDR_STAGE_TILE_SORT, s);
         GDR_CUDA(gdr::launch_tile_sort_surfel(W, H, surfel_state, img, (uint64_t*)sort_scratch,
-                                              P > 0 ? tile_capacity : 32, surfel_stream, capacity, s),
+                                              P > 0 ? tile_capacity : 32, P > 0 ? tile_offsets : nullptr, surfel_stream,
+                                              capacity, s),
                  "tile_sort");
     }
     {

@@ -86,8 +86,8 @@ __device__ __forceinline__ int lower_bound_u64(const uint64_t* a, int n, uint64_
 template <int RQ>
 __global__ void __launch_bounds__(SORT_THREADS)
 tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t* keys0, float4* __restrict__ stream0,
-                 int64_t capacity, uint32_t tile_cap, size_t keys_stride, size_t geom_stride, size_t img_stride, int gx,
-                 int T) {
+                 int64_t capacity, uint32_t tile_cap, const uint32_t* __restrict__ tile_base0, size_t keys_stride,
+                 size_t geom_stride, size_t img_stride, int gx, int T) {
     __shared__ uint64_t s_keys[SORT_CHUNK];
     __shared__ uint32_t s_cnt[BUCKETS];        // bucket histogram, then fill cursors
     __shared__ uint32_t s_start[BUCKETS + 1];  // exclusive scan of the histogram
@@ -101,7 +101,10 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
     const ImageState img = img0.at(v, img_stride);
     float4* __restrict__ stream = stream0 + (size_t)v * capacity * RQ;
     const int tile = blockIdx.x;
-    const uint32_t n_binned = min(img.tile_count[(size_t)tile * COUNT_STRIDE], tile_cap);  // claims beyond the segment were not stored
+    size_t seg_first;
+    uint32_t seg_cap;
+    tile_segment(tile_base0 ? tile_base0 + (size_t)v * (T + 1) : nullptr, tile_cap, tile, seg_first, seg_cap);
+    const uint32_t n_binned = min(img.tile_count[(size_t)tile * COUNT_STRIDE], seg_cap);  // claims beyond the segment were not stored
     if (n_binned == 0) {  // an empty tile: no stream range, last in the blend kernels' order
         if (threadIdx.x == 0) {
             img.tile_range[tile] = make_uint2(0u, 0u);
@@ -125,7 +128,7 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
         }
     };
     const int n = (int)n_binned;
-    uint64_t* seg = keys0 + (size_t)v * keys_stride + (size_t)tile * tile_cap;
+    uint64_t* seg = keys0 + (size_t)v * keys_stride + seg_first;
     const uint64_t* sorted;  // where the sorted keys end up (shared memory or `seg`)
     uint64_t* alt = nullptr;
     if (n > BUCKET_MAX) {
@@ -392,24 +395,67 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
     pdl_trigger();  // the forward blend may start launching (empty tiles left above: exiting counts as a trigger)
 }
 
+// One CTA per view: exclusive scan of the per-tile instance counts (the exact key layout of state.cuh).  Only runs
+// after a projection whose uniform segments overflowed, or for scenes whose uniform segments would waste memory.
+__global__ void tile_offsets_kernel(int T, ImageState img0, size_t img_stride, uint32_t* __restrict__ offsets0) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const ImageState img = img0.at(blockIdx.x, img_stride);
+    uint32_t* __restrict__ offsets = offsets0 + (size_t)blockIdx.x * (T + 1);
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < T; base += blockDim.x) {
+        const int t = base + threadIdx.x;
+        const uint32_t n = t < T ? img.tile_count[(size_t)t * COUNT_STRIDE] : 0u;
+        const int incl = warp_incl_scan((int)n);
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = (uint32_t)incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const uint32_t ws = threadIdx.x < (blockDim.x >> 5) ? s_warp[threadIdx.x] : 0u;
+            s_warp[threadIdx.x] = (uint32_t)warp_incl_scan((int)ws) - ws;
+        }
+        __syncthreads();
+        const uint32_t begin = s_carry + s_warp[threadIdx.x >> 5] + (uint32_t)incl - n;
+        if (t < T) offsets[t] = begin;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = begin + n;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[T] = s_carry;
+}
+
 }  // namespace
 
+size_t key_bytes_per_view(int W, int H, int64_t tile_cap, bool exact) {
+    // exact layout: tile_cap is the number of keys of one view's region (>= the largest R of the batch)
+    return exact ? align_up((size_t)tile_cap * sizeof(uint64_t), 256) : sort_scratch_bytes(W, H, tile_cap);
+}
+
+cudaError_t launch_tile_offsets(int W, int H, ImageState img, uint32_t* tile_offsets, const Views& vw, cudaStream_t s) {
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    tile_offsets_kernel<<<max(1, vw.V), 1024, 0, s>>>(gx * gy, img, vw.img_stride, tile_offsets);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint64_t* keys, int64_t tile_cap,
-                             Splat* stream, int64_t capacity, const Views& vw, cudaStream_t s) {
+                             const uint32_t* tile_base, Splat* stream, int64_t capacity, const Views& vw,
+                             cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     return launch_dependent(tile_sort_kernel<3>, dim3(gx * gy, max(1, vw.V)), dim3(SORT_THREADS), 0, s,
                             reinterpret_cast<const float4*>(geom.splat), img, keys, reinterpret_cast<float4*>(stream),
-                            capacity, (uint32_t)tile_cap, sort_scratch_bytes(W, H, tile_cap) / sizeof(uint64_t),
-                            vw.geom_stride, vw.img_stride, gx, gx * gy);
+                            capacity, (uint32_t)tile_cap, tile_base,
+                            key_bytes_per_view(W, H, tile_cap, tile_base != nullptr) / sizeof(uint64_t), vw.geom_stride,
+                            vw.img_stride, gx, gx * gy);
 }
 
 cudaError_t launch_tile_sort_surfel(int W, int H, const void* surfel_records, ImageState img, uint64_t* keys,
-                                    int64_t tile_cap, void* surfel_stream, int64_t capacity, cudaStream_t s) {
+                                    int64_t tile_cap, const uint32_t* tile_base, void* surfel_stream, int64_t capacity,
+                                    cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     return launch_dependent(tile_sort_kernel<5>, dim3(gx * gy, 1), dim3(SORT_THREADS), 0, s,
                             reinterpret_cast<const float4*>(surfel_records), img, keys,
-                            reinterpret_cast<float4*>(surfel_stream), capacity, (uint32_t)tile_cap, (size_t)0, (size_t)0,
-                            (size_t)0, gx, gx * gy);
+                            reinterpret_cast<float4*>(surfel_stream), capacity, (uint32_t)tile_cap, tile_base, (size_t)0,
+                            (size_t)0, (size_t)0, gx, gx * gy);
 }
 
 }  // namespace gdr

@@ -52,7 +52,8 @@ struct ProjectArgs {
     ImageState img;
     uint64_t* keys;      // [V][T][tile_cap] key segments (SortScratch, state.cuh)
     size_t keys_stride;  // keys between consecutive views
-    uint32_t tile_cap;   // slots per tile segment
+    uint32_t tile_cap;   // slots per tile segment (uniform layout)
+    const uint32_t* tile_base;  // [V][T + 1] exact layout (see SortScratch in state.cuh), or nullptr
     int32_t* counts_host;  // device-accessible pinned host memory [V][4] or nullptr (see report_counts)
 };
 
@@ -65,11 +66,17 @@ cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewma
 // Batched layout (V = vw.V views, blockIdx.y = view): every view has its own key segments (T x tile_cap keys) and
 // `capacity` stream records, back to back; images are [V][C][H][W]; radii [V][P]; accum [V][P][12].
 cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint64_t* keys, int64_t tile_cap,
-                             Splat* stream, int64_t capacity, const Views& vw, cudaStream_t s);
+                             const uint32_t* tile_base, Splat* stream, int64_t capacity, const Views& vw,
+                             cudaStream_t s);
+// exclusive scan of a view's per-tile instance counts -> tile_offsets[T + 1] (the exact key layout)
+cudaError_t launch_tile_offsets(int W, int H, ImageState img, uint32_t* tile_offsets, const Views& vw, cudaStream_t s);
+// bytes of one view's key segments in either layout
+size_t key_bytes_per_view(int W, int H, int64_t tile_cap, bool exact);
 
 // The same per-tile sort with 80-byte Surfel records (surfel.cuh) gathered into the stream; single view.
 cudaError_t launch_tile_sort_surfel(int W, int H, const void* surfel_records, ImageState img, uint64_t* keys,
-                                    int64_t tile_cap, void* surfel_stream, int64_t capacity, cudaStream_t s);
+                                    int64_t tile_cap, const uint32_t* tile_base, void* surfel_stream, int64_t capacity,
+                                    cudaStream_t s);
 
 // blend_fwd.cu
 // hwc_clamp: write out_color as the clamped [H][W][3] image of Renderer.render_img (GDR_FLAG_FUSED_EPILOGUE)
@@ -126,8 +133,8 @@ cudaError_t launch_surfel_project(int P, int sh_degree, int M, int W, int H, con
                                   int scale_stride, float scale_modifier, const float* rotations,
                                   const float* transmat_precomp, const float* view, const float* proj,
                                   const float* campos, int32_t* radii, GeomState geom, void* surfel_state,
-                                  ImageState img, uint64_t* keys, int64_t tile_cap, int32_t* counts_host,
-                                  cudaStream_t s);
+                                  ImageState img, uint64_t* keys, int64_t tile_cap, const uint32_t* tile_base,
+                                  int32_t* counts_host, cudaStream_t s);
 cudaError_t launch_surfel_blend_forward(int W, int H, ImageState img, const void* stream, int64_t capacity,
                                         const float* bg, float* out_color, float* out_allmap, float* aux,
                                         cudaStream_t s);

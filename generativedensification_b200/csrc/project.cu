@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs
     target.tile_count = img.tile_count;
     target.keys = a.keys + (size_t)v * a.keys_stride;
     target.tile_cap = a.tile_cap;
+    target.tile_base = a.tile_base ? a.tile_base + (size_t)v * (a.gx * a.gy + 1) : nullptr;
     target.gx = a.gx;
     __shared__ uint32_t s_tot[2];
     __shared__ __align__(8) uint64_t bar;

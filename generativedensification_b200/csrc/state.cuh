@@ -19,8 +19,14 @@
 //     uint32   order[33][T]             tiles grouped by floor(log2(count)) + 1 (bucket 0 = empty tiles), filled by
 //                                       tile_sort; the blend kernels walk the buckets from the heaviest down
 //     uint32   n_contrib[H * W]
-// SortScratch (temporary): uint64 keys[T][tile_capacity]  -- key = depth bits << 32 | Gaussian index; a tile's
-//                                       segment has a fixed capacity chosen by the host from the previous frame
+// SortScratch (temporary): uint64 keys -- key = depth bits << 32 | Gaussian index.  Two layouts:
+//     uniform  keys[T][tile_capacity]   every tile's segment has the same capacity, predicted by the host from the
+//                                       previous frame (the steady state: one projection pass, no prefix sum);
+//     exact    keys[R], tile t's segment = [tile_offsets[t], tile_offsets[t + 1])  with tile_offsets the exclusive scan
+//                                       of the per-tile counts a first projection pass measured (gdr_tile_offsets) --
+//                                       taken when the prediction failed (first frame of a scene size, or a jump of the
+//                                       densest tile) or when uniform segments would waste memory (a few very dense
+//                                       tiles): exactly R keys, for any distribution
 // SplatStream (reference: BinningState.point_list, but materialised):
 //     Splat    stream[capacity]         per-tile, depth-sorted copies of the Gaussians' records,
 //                                       contiguous per tile so a tile is staged with cp.async.bulk

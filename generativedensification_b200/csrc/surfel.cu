@@ -59,6 +59,7 @@ struct SurfelProjectArgs {
     ImageState img;
     uint64_t* keys;     // [T][tile_cap] key segments (SortScratch, state.cuh)
     uint32_t tile_cap;
+    const uint32_t* tile_base;  // exact key layout [T + 1], or nullptr (state.cuh)
     int32_t* counts_host;  // device-accessible pinned host memory [4] or nullptr
 };
 
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(SP_THREADS) surfel_project_kernel(const Surfel
     target.tile_count = a.img.tile_count;
     target.keys = a.keys;
     target.tile_cap = a.tile_cap;
+    target.tile_base = a.tile_base;
     target.gx = a.gx;
     if (threadIdx.x == 0) s_tot[0] = s_tot[1] = 0u;
     __syncthreads();
@@ -747,8 +749,8 @@ cudaError_t launch_surfel_project(int P, int sh_degree, int M, int W, int H, con
                                   int scale_stride, float scale_modifier, const float* rotations,
                                   const float* transmat_precomp, const float* view, const float* proj,
                                   const float* campos, int32_t* radii, GeomState geom, void* surfel_state,
-                                  ImageState img, uint64_t* keys, int64_t tile_cap, int32_t* counts_host,
-                                  cudaStream_t s) {
+                                  ImageState img, uint64_t* keys, int64_t tile_cap, const uint32_t* tile_base,
+                                  int32_t* counts_host, cudaStream_t s) {
     if (P <= 0) return cudaSuccess;
     SurfelProjectArgs a;
     a.P = P; a.sh_degree = sh_degree; a.M = M; a.W = W; a.H = H;
@@ -757,7 +759,7 @@ cudaError_t launch_surfel_project(int P, int sh_degree, int M, int W, int H, con
     a.scale_stride = scale_stride; a.scale_modifier = scale_modifier; a.rotations = rotations;
     a.transmat_precomp = transmat_precomp; a.view = view; a.proj = proj; a.campos = campos;
     a.radii = radii; a.geom = geom; a.surfel = (Surfel*)surfel_state; a.img = img;
-    a.keys = keys; a.tile_cap = (uint32_t)tile_cap; a.counts_host = counts_host;
+    a.keys = keys; a.tile_cap = (uint32_t)tile_cap; a.tile_base = tile_base; a.counts_host = counts_host;
     const int n_vblocks = (P + SP_THREADS - 1) / SP_THREADS;
     const int grid = min(n_vblocks, sm_count() * 8);
     surfel_project_kernel<<<grid, SP_THREADS, 0, s>>>(a);

@@ -37,11 +37,24 @@ static_assert(sizeof(EmitRec) == 64, "EmitRec must be 64 bytes");
 constexpr int EMIT_DEPTH = GDR_EMIT_DEPTH;  // 32-pair windows whose slot claims are in flight together
 
 struct EmitTarget {
-    uint32_t* tile_count;  // [T * COUNT_STRIDE] of this view
-    uint64_t* keys;        // [T][tile_cap] of this view; T < 2^24 (checked at the API)
-    uint32_t tile_cap;
+    uint32_t* tile_count;       // [T * COUNT_STRIDE] of this view
+    uint64_t* keys;             // this view's key segments; T < 2^24 (checked at the API)
+    uint32_t tile_cap;          // uniform layout: tile t's segment is keys[t * tile_cap .. + tile_cap)
+    const uint32_t* tile_base;  // exact layout (non-null): tile t's segment is keys[tile_base[t] .. tile_base[t + 1])
     int gx;
 };
+
+// Where tile `tile`'s key segment starts and how many keys it holds (see SortScratch in state.cuh).
+__device__ __forceinline__ void tile_segment(const uint32_t* __restrict__ tile_base, uint32_t tile_cap, int tile,
+                                             size_t& first, uint32_t& cap) {
+    if (tile_base) {
+        first = tile_base[tile];
+        cap = tile_base[tile + 1] - tile_base[tile];
+    } else {
+        first = (size_t)tile * tile_cap;
+        cap = tile_cap;
+    }
+}
 
 // All 32 lanes call.  `kept` / `max_fill` accumulate this lane's binned pairs and the largest slot + 1 it claimed.
 // CULL: drop pairs whose tile the splat provably cannot reach with alpha >= 1/255 (splat_misses_rect, exact).
@@ -114,8 +127,10 @@ __device__ __forceinline__ void warp_emit_tiles(EmitRec* __restrict__ s_rec, int
         for (int s = 0; s < EMIT_DEPTH; s++) {
             if (where[s] != 0xffffffffu) {
                 const uint2 key = s_rec[where[s] >> 24].key;
-                if (pos[s] < t.tile_cap)
-                    t.keys[(size_t)(where[s] & 0xffffffu) * t.tile_cap + pos[s]] = ((uint64_t)key.y << 32) | key.x;
+                size_t first;
+                uint32_t cap;
+                tile_segment(t.tile_base, t.tile_cap, (int)(where[s] & 0xffffffu), first, cap);
+                if (pos[s] < cap) t.keys[first + pos[s]] = ((uint64_t)key.y << 32) | key.x;
                 max_fill = max(max_fill, pos[s] + 1u);
                 kept += 1u;
             }

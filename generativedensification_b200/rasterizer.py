@@ -173,41 +173,53 @@ def _mailbox(device, V: int = 1) -> Mailbox:
     return mb["ring"][i]
 
 
-def drive_forward(key, mailbox: Mailbox, stream, project, render):
+UNIFORM_BYTES_FLOOR = 1 << 30
+
+
+def drive_forward(key, mailbox: Mailbox, stream, project, render, tile_offsets, n_tiles: int):
     """The host protocol shared by every forward entry (single view, batched views, surfels).
 
-    project(tile_capacity) enqueues the projection + binning kernel, whose last CTA writes the counts into
-    `mailbox`, and returns the key-segment scratch it allocated; render(scratch, tile_capacity, capacity, rerun)
-    enqueues tile sort + blend.  The render is enqueued speculatively with the capacities predicted from the
-    previous frame of the same `key`, then the host polls for the projection kernel's counts ONLY and repeats what
-    a mis-prediction invalidated.  Returns the mailbox rows as lists."""
+    project(tile_capacity, offsets) enqueues the projection + binning kernel, whose last CTA writes the counts into
+    `mailbox`, and returns the key scratch it allocated; render(scratch, tile_capacity, offsets, capacity, rerun)
+    enqueues tile sort + blend; tile_offsets() returns the exclusive scan of the per-tile counts the last projection
+    left (device int32 [V, n_tiles + 1], gdr_tile_offsets).
+
+    Steady state: uniform key segments sized from the previous frame of the same `key` and a speculative render, both
+    enqueued before the host polls for the projection kernel's counts ONLY.  If a tile overflowed its segment (first
+    frame of a scene size, or the densest tile more than doubled) the frame is projected again into the EXACT layout
+    (per-tile offsets from the counts just measured: R keys whatever the distribution); scenes whose uniform segments
+    would waste memory (a few tiles far denser than the rest) take that two-pass route every frame.  Returns the
+    mailbox rows as lists."""
+    V = mailbox.words.shape[0]
     tile_cap = _predictor.predict_tile(key)
     guess = _predictor.predict(key)
+    last_r = _predictor.last.get(key)
+    if last_r is not None and V * n_tiles * tile_cap * 8 > max(UNIFORM_BYTES_FLOOR, 24 * 8 * last_r * V):
+        tile_cap, guess = 32, 0  # uniform segments would be mostly air: count first, then the exact layout
     mailbox.reset()
-    scratch = project(tile_cap)
+    scratch = project(tile_cap, None)
     if guess > 0:
-        render(scratch, tile_cap, guess, False)  # speculative: the GPU keeps working while the host waits for R
+        render(scratch, tile_cap, None, guess, False)  # speculative: the GPU keeps working while the host waits for R
     rows = mailbox.wait(stream)  # the projection kernel only, not the frame
     rendered = guess > 0
+    offsets = None
     max_tile = max(r[_lib.COUNT_MAX_TILE] for r in rows)
+    r_max = max(r[_lib.COUNT_RENDERED] for r in rows)
     stats["forwards"] += 1
     if max_tile > tile_cap:
-        # a tile received more instances than its key segment holds (first frame of a new scene size, or the
-        # densest tile more than doubled): the dropped keys are gone -- project again with room for them
         stats["reprojected"] += 1
-        tile_cap = round_tile_capacity(max_tile + max_tile // 4)
+        offsets = tile_offsets()
+        tile_cap = max(32, (r_max + 31) // 32 * 32)  # exact layout: the size of one view's key region
         mailbox.reset()
-        scratch = project(tile_cap)
-        rows = mailbox.wait(stream)
-        max_tile = max(r[_lib.COUNT_MAX_TILE] for r in rows)
+        scratch = project(tile_cap, offsets)
+        rows = mailbox.wait(stream)  # the same counts again
         rendered = False
-    r_max = max(r[_lib.COUNT_RENDERED] for r in rows)
     _predictor.update(key, r_max, max_tile)
     if not rendered:
-        render(scratch, tile_cap, round_capacity(r_max), False)
+        render(scratch, tile_cap, offsets, round_capacity(r_max), False)
     elif r_max > guess:
         stats["rerendered"] += 1
-        render(scratch, tile_cap, round_capacity(r_max), True)
+        render(scratch, tile_cap, offsets, round_capacity(r_max), True)
     return rows
 
 
@@ -268,27 +280,35 @@ def _forward_impl(settings: GaussianRasterizationSettings, means3D, sh, colors_p
         depth = torch.empty(1, H, W, **f32)
         alpha = torch.empty(1, H, W, **f32)
 
-        def project(tile_capacity: int):
-            scratch = torch.empty(_lib.query_bytes("gdr_sort_scratch_bytes", W, H, tile_capacity), dtype=torch.uint8,
-                                  device=device)
+        n_tiles = ((W + 15) // 16) * ((H + 15) // 16)
+
+        def project(tile_capacity: int, offsets):
+            nbytes = (_lib.query_bytes("gdr_sort_scratch_bytes", W, H, tile_capacity) if offsets is None else
+                      _lib.query_bytes("gdr_sort_scratch_exact_bytes", tile_capacity))
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
             _lib.check(lib.gdr_forward_project(
                 P, int(settings.sh_degree), st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp),
                 _ptr(opacities), _ptr(scales), float(settings.scale_modifier), _ptr(rotations), _ptr(cov3Ds_precomp),
                 _ptr(view), _ptr(proj), _ptr(campos), float(settings.tanfovx), float(settings.tanfovy),
                 int(bool(settings.prefiltered)), radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(),
-                scratch.data_ptr(), tile_capacity, mailbox.ptr, flags, sptr), "gdr_forward_project")
+                scratch.data_ptr(), tile_capacity, _ptr(offsets), mailbox.ptr, flags, sptr), "gdr_forward_project")
             return scratch
 
-        def render(scratch, tile_capacity: int, capacity: int, rerun: bool):
+        def render(scratch, tile_capacity: int, offsets, capacity: int, rerun: bool):
             st.capacity = capacity
             st.stream_buf = torch.empty(_lib.query_bytes("gdr_splat_stream_bytes", capacity), dtype=torch.uint8,
                                         device=device)
             _lib.check(lib.gdr_forward_render(
                 P, W, H, _ptr(bg), st.geom.data_ptr(), st.img.data_ptr(), st.stream_buf.data_ptr(),
-                scratch.data_ptr(), tile_capacity, capacity, color.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
-                flags | (_lib.FLAG_RERUN if rerun else 0), sptr), "gdr_forward_render")
+                scratch.data_ptr(), tile_capacity, _ptr(offsets), capacity, color.data_ptr(), depth.data_ptr(),
+                alpha.data_ptr(), flags | (_lib.FLAG_RERUN if rerun else 0), sptr), "gdr_forward_render")
 
-        rows = drive_forward(key, mailbox, stream, project, render)
+        def tile_offsets():
+            offsets = torch.empty(1, n_tiles + 1, dtype=torch.int32, device=device)
+            _lib.check(lib.gdr_tile_offsets(1, W, H, st.img.data_ptr(), offsets.data_ptr(), sptr), "gdr_tile_offsets")
+            return offsets
+
+        rows = drive_forward(key, mailbox, stream, project, render, tile_offsets, n_tiles)
         st.num_rendered = rows[0][_lib.COUNT_RENDERED]
         if settings.prefiltered and (rows[0][_lib.COUNT_FLAGS] & _lib.COUNT_FLAG_PREFILTERED):
             # the reference printf()s this and traps on the device (auxiliary.h:154-158); here the context survives

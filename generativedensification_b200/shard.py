@@ -174,6 +174,10 @@ class HostFeeder:
         i = self.head
         if self.slots[i] is None or any(self.slots[i][k].shape != v.shape for k, v in host.items()):
             self.slots[i] = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
+            # The caching allocator may hand out blocks the compute stream freed while kernels that use them are still
+            # queued there (reuse is stream-ordered on the ALLOCATING stream only): the copy stream must not write
+            # them before that work has drained.  (Only on (re)allocation; afterwards the slot is ours.)
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.copy_stream):
             if self.free[i] is not None:
                 self.copy_stream.wait_event(self.free[i])  # the renders that read this slot have finished

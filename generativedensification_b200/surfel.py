@@ -100,27 +100,36 @@ def _forward_impl(settings, means3D, sh, colors_precomp, opacities, scales, rota
         color = torch.empty(3, H, W, **f32)
         allmap = torch.empty(7, H, W, **f32)
 
-        def project(tile_capacity: int):
-            scratch = torch.empty(_lib.query_bytes("gdr_sort_scratch_bytes", W, H, tile_capacity), **u8)
+        n_tiles = ((W + 15) // 16) * ((H + 15) // 16)
+
+        def project(tile_capacity: int, offsets):
+            nbytes = (_lib.query_bytes("gdr_sort_scratch_bytes", W, H, tile_capacity) if offsets is None else
+                      _lib.query_bytes("gdr_sort_scratch_exact_bytes", tile_capacity))
+            scratch = torch.empty(nbytes, **u8)
             _lib.check(lib.gdr_surfel_forward_project(
                 P, int(settings.sh_degree), st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp),
                 _ptr(opacities), _ptr(scales), st.scale_stride, float(settings.scale_modifier), _ptr(rotations),
                 _ptr(transmat_precomp), _ptr(view), _ptr(proj), _ptr(campos), radii.data_ptr(), st.geom.data_ptr(),
-                st.surfel.data_ptr(), st.img.data_ptr(), scratch.data_ptr(), tile_capacity, mailbox.ptr, sptr),
-                "gdr_surfel_forward_project")
+                st.surfel.data_ptr(), st.img.data_ptr(), scratch.data_ptr(), tile_capacity, _ptr(offsets), mailbox.ptr,
+                sptr), "gdr_surfel_forward_project")
             return scratch
 
-        def render(scratch, tile_capacity: int, capacity: int, rerun: bool):
+        def render(scratch, tile_capacity: int, offsets, capacity: int, rerun: bool):
             st.capacity = capacity
             st.stream_buf = torch.empty(_lib.query_bytes("gdr_surfel_stream_bytes", capacity), **u8)
             _lib.check(lib.gdr_surfel_forward_render(
                 P, W, H, _ptr(bg), st.geom.data_ptr(), st.surfel.data_ptr(), st.img.data_ptr(),
-                st.stream_buf.data_ptr(), scratch.data_ptr(), tile_capacity, capacity, color.data_ptr(),
+                st.stream_buf.data_ptr(), scratch.data_ptr(), tile_capacity, _ptr(offsets), capacity, color.data_ptr(),
                 allmap.data_ptr(), st.aux.data_ptr(), _lib.FLAG_RERUN if rerun else 0, sptr),
                 "gdr_surfel_forward_render")
 
+        def tile_offsets():
+            offsets = torch.empty(1, n_tiles + 1, dtype=torch.int32, device=device)
+            _lib.check(lib.gdr_tile_offsets(1, W, H, st.img.data_ptr(), offsets.data_ptr(), sptr), "gdr_tile_offsets")
+            return offsets
+
         # speculative, as in the 3DGS module: the GPU keeps working while the host learns the counts
-        rows = drive_forward((device.index, P, H, W, "surfel"), mailbox, stream, project, render)
+        rows = drive_forward((device.index, P, H, W, "surfel"), mailbox, stream, project, render, tile_offsets, n_tiles)
         st.num_rendered = rows[0][_lib.COUNT_RENDERED]
     return color, radii, allmap, st
 

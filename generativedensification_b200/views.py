@@ -115,27 +115,35 @@ def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scal
         render_flags = flags | (_lib.FLAG_FUSED_EPILOGUE if fused_epilogue else 0)
         one_view = _lib.query_bytes
 
-        def project(tile_capacity: int):
-            scratch = torch.empty(V * one_view("gdr_sort_scratch_bytes", W, H, tile_capacity), dtype=torch.uint8,
-                                  device=device)
+        n_tiles = ((W + 15) // 16) * ((H + 15) // 16)
+
+        def project(tile_capacity: int, offsets):
+            nbytes = (one_view("gdr_sort_scratch_bytes", W, H, tile_capacity) if offsets is None else
+                      one_view("gdr_sort_scratch_exact_bytes", tile_capacity))
+            scratch = torch.empty(V * nbytes, dtype=torch.uint8, device=device)
             _lib.check(lib.gdr_views_forward_project(
                 V, P, cb.sh_degree, st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
                 _ptr(scales), cb.scale_modifier, _ptr(rotations), _ptr(cov3Ds_precomp), cb.cams.data_ptr(),
                 int(cb.prefiltered), radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(), scratch.data_ptr(),
-                tile_capacity, mailbox.ptr, flags, sptr), "gdr_views_forward_project")
+                tile_capacity, _ptr(offsets), mailbox.ptr, flags, sptr), "gdr_views_forward_project")
             return scratch
 
-        def render(scratch, tile_capacity: int, capacity: int, rerun: bool):
+        def render(scratch, tile_capacity: int, offsets, capacity: int, rerun: bool):
             st.capacity = capacity
             st.stream_buf = torch.empty(_lib.query_bytes("gdr_splat_stream_bytes", V * capacity), dtype=torch.uint8,
                                         device=device)
             _lib.check(lib.gdr_views_forward_render(
                 V, P, W, H, cb.cams.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(), st.stream_buf.data_ptr(),
-                scratch.data_ptr(), tile_capacity, capacity, color.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
-                render_flags | (_lib.FLAG_RERUN if rerun else 0), sptr), "gdr_views_forward_render")
+                scratch.data_ptr(), tile_capacity, _ptr(offsets), capacity, color.data_ptr(), depth.data_ptr(),
+                alpha.data_ptr(), render_flags | (_lib.FLAG_RERUN if rerun else 0), sptr), "gdr_views_forward_render")
+
+        def tile_offsets():
+            offsets = torch.empty(V, n_tiles + 1, dtype=torch.int32, device=device)
+            _lib.check(lib.gdr_tile_offsets(V, W, H, st.img.data_ptr(), offsets.data_ptr(), sptr), "gdr_tile_offsets")
+            return offsets
 
         key = (device.index, P, H, W, flags, "views", V)
-        rows = drive_forward(key, mailbox, stream, project, render)  # ONE host wait per batch
+        rows = drive_forward(key, mailbox, stream, project, render, tile_offsets, n_tiles)  # ONE host wait per batch
         st.num_rendered = [r[_lib.COUNT_RENDERED] for r in rows]
         if cb.prefiltered and any(r[_lib.COUNT_FLAGS] & _lib.COUNT_FLAG_PREFILTERED for r in rows):
             raise RuntimeError(PREFILTERED_MESSAGE)

@@ -122,6 +122,8 @@ GDR_API int gdr_splat_stream_bytes(int64_t capacity, int64_t* bytes); /* depth-s
 GDR_API int gdr_sort_scratch_bytes(int W, int H, int64_t tile_capacity, int64_t* bytes); /* per view; temporary: tiles x
                                                                          tile_capacity 8-byte keys (tile_capacity a positive
                                                                          multiple of 32), free after gdr_forward_render */
+GDR_API int gdr_sort_scratch_exact_bytes(int64_t num_keys, int64_t* bytes); /* per view, the exact key layout (below):
+                                                                         num_keys (a positive multiple of 32, >= R) keys */
 GDR_API int gdr_backward_scratch_bytes(int P, int64_t* bytes);        /* temporary screen-space gradient accumulators */
 
 /* Step 1 of the forward (replaces the first half of Rasterizer::forward, rasterizer_impl.cu:197-282). */
@@ -132,15 +134,28 @@ GDR_API int gdr_forward_project(int P, int sh_degree, int M, int W, int H,
                         const float* viewmatrix, const float* projmatrix, const float* campos,
                         float tan_fovx, float tan_fovy, int prefiltered,
                         int32_t* radii /* out [P] */, void* geom_state, void* image_state,
-                        void* sort_scratch, int64_t tile_capacity,
+                        void* sort_scratch, int64_t tile_capacity, const uint32_t* tile_offsets /* NULL: uniform layout */,
                         int32_t* counts_host /* pinned host memory [4] or NULL */, int flags, void* stream);
+
+/* The two layouts of the key segments in sort_scratch (both steps of a frame must use the same):
+ *   uniform (tile_offsets == NULL)  tile t owns keys [t * tile_capacity, (t + 1) * tile_capacity): one projection pass,
+ *       nothing to scan -- the steady state, with tile_capacity predicted from the previous frame's
+ *       GDR_COUNT_MAX_TILE.  A tile that receives more instances keeps counting (GDR_COUNT_MAX_TILE is exact) but
+ *       drops the keys: project again.
+ *   exact (tile_offsets != NULL)    tile t owns keys [tile_offsets[t], tile_offsets[t + 1]) and `tile_capacity` is the
+ *       size of one view's key region (a multiple of 32, >= R; gdr_sort_scratch_exact_bytes).  tile_offsets comes from
+ *       gdr_tile_offsets, which scans the per-tile counts a previous projection pass of the SAME inputs left in
+ *       image_state: exactly R keys whatever the distribution -- the way out when the prediction failed, and the layout
+ *       for scenes whose densest tile is so far above the average that uniform segments would waste memory.
+ * gdr_tile_offsets: V = 1 for the single-view entry points; tile_offsets is device memory, [V][tiles + 1] uint32. */
+GDR_API int gdr_tile_offsets(int V, int W, int H, const void* image_states, uint32_t* tile_offsets, void* stream);
 
 /* Step 2 of the forward (replaces rasterizer_impl.cu:304-337). out_* are [3,H,W], [1,H,W], [1,H,W].
  * sort_scratch / tile_capacity are the ones step 1 filled. */
 GDR_API int gdr_forward_render(int P, int W, int H, const float* bg,
                        const void* geom_state, void* image_state,
-                       void* splat_stream, void* sort_scratch, int64_t tile_capacity, int64_t capacity,
-                       float* out_color, float* out_depth, float* out_alpha, int flags, void* stream);
+                       void* splat_stream, void* sort_scratch, int64_t tile_capacity, const uint32_t* tile_offsets,
+                       int64_t capacity, float* out_color, float* out_depth, float* out_alpha, int flags, void* stream);
 
 /* Backward (replaces Rasterizer::backward, rasterizer_impl.cu:343-447).  dL_dout_depth / dL_dout_alpha
  * may be NULL (treated as zero).  Output gradient pointers may be NULL when the matching bit of
@@ -192,11 +207,12 @@ GDR_API int gdr_views_forward_project(int V, int P, int sh_degree, int M, int W,
                         const float* rotations, const float* cov3D_precomp,
                         const gdr_camera* cameras /* device [V] */, int prefiltered,
                         int32_t* radii /* out [V][P] */, void* geom_states, void* image_states,
-                        void* sort_scratch, int64_t tile_capacity,
+                        void* sort_scratch, int64_t tile_capacity, const uint32_t* tile_offsets /* [V][tiles+1] or NULL */,
                         int32_t* counts_host /* pinned [V][4] or NULL */, int flags, void* stream);
 GDR_API int gdr_views_forward_render(int V, int P, int W, int H, const gdr_camera* cameras,
                         const void* geom_states, void* image_states, void* splat_streams, void* sort_scratch,
-                        int64_t tile_capacity, int64_t capacity_per_view, float* out_color /*[V,3,H,W]*/,
+                        int64_t tile_capacity, const uint32_t* tile_offsets, int64_t capacity_per_view,
+                        float* out_color /*[V,3,H,W]*/,
                         float* out_depth /*[V,1,H,W]*/, float* out_alpha /*[V,1,H,W]*/, int flags, void* stream);
 GDR_API int gdr_views_backward(int V, int P, int sh_degree, int M, int W, int H,
                         const float* means3D, const float* shs, const float* colors_precomp,
@@ -255,14 +271,14 @@ GDR_API int gdr_surfel_forward_project(int P, int sh_degree, int M, int W, int H
                         const float* rotations, const float* transmat_precomp,
                         const float* viewmatrix, const float* projmatrix, const float* campos,
                         int32_t* radii /* out [P] */, void* geom_state, void* surfel_state, void* image_state,
-                        void* sort_scratch, int64_t tile_capacity,
+                        void* sort_scratch, int64_t tile_capacity, const uint32_t* tile_offsets,
                         int32_t* counts_host /* pinned host memory [4] or NULL */, void* stream);
 
 /* out_color [3,H,W], out_allmap [7,H,W].  flags: 0 or GDR_FLAG_RERUN. */
 GDR_API int gdr_surfel_forward_render(int P, int W, int H, const float* bg,
                         const void* geom_state, const void* surfel_state, void* image_state,
-                        void* surfel_stream, void* sort_scratch, int64_t tile_capacity, int64_t capacity,
-                        float* out_color, float* out_allmap, void* surfel_aux, int flags, void* stream);
+                        void* surfel_stream, void* sort_scratch, int64_t tile_capacity, const uint32_t* tile_offsets,
+                        int64_t capacity, float* out_color, float* out_allmap, void* surfel_aux, int flags, void* stream);
 
 /* dL_dout_allmap may be NULL (zero).  Any output pointer may be NULL; requested outputs are fully written.
  * dL_dmeans2D is [P, means2D_cols] (3 or 4): columns 0:2 = the densification statistic of 2DGS (gradient w.r.t. the

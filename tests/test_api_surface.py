@@ -133,7 +133,7 @@ def test_library_exports_every_declared_symbol():
     assert _lib.query_bytes("gdr_surfel_aux_bytes", 8, 8) >= 12 * 64
     nul = ctypes.c_void_p(None)
     project_args = lambda P, img, tile_cap=1024: (P, 1, 4, 64, 64, nul, nul, nul, nul, nul, 1.0, nul, nul, nul, nul, nul,
-                                                  1.0, 1.0, 0, nul, nul, img, nul, tile_cap, nul, 0, nul)
+                                                  1.0, 1.0, 0, nul, nul, img, nul, tile_cap, nul, nul, 0, nul)
     assert lib.gdr_forward_project(*project_args(-1, nul)) == -1
     assert lib.gdr_forward_project(*project_args(1 << 28, nul)) == -3
     assert b"2^28" in lib.gdr_last_error()
@@ -141,7 +141,8 @@ def test_library_exports_every_declared_symbol():
     # the per-tile key-segment capacity must be a positive multiple of 32
     assert _lib.query_bytes("gdr_sort_scratch_bytes", 800, 800, 1024) == 2500 * 1024 * 8
     assert raw.gdr_sort_scratch_bytes(800, 800, ctypes.c_int64(1000), ctypes.byref(out)) < 0
-    assert lib.gdr_forward_render(10, 64, 64, nul, nul, nul, nul, nul, 1024, 1 << 33, nul, nul, nul, 0, nul) == -1
+    assert lib.gdr_forward_render(10, 64, 64, nul, nul, nul, nul, nul, 1024, nul, 1 << 33, nul, nul, nul, 0, nul) == -1
+    assert _lib.query_bytes("gdr_sort_scratch_exact_bytes", 1024) == 8192
     assert lib.gdr_surfel_backward(10, 1, 4, 64, 64, *([nul] * 3), nul, nul, 3, 1.0, *([nul] * 10), 0, *([nul] * 5), 5,
                                    *([nul] * 9)) == -1
 

@@ -185,16 +185,30 @@ def test_capacity_misprediction_is_rerun(device):
     c = _render(sc, device)
     for x, y in zip(a, c):
         assert torch.equal(x, y)
-    # a per-tile key segment far too small: the projection is repeated with room for the densest tile
+    # a per-tile key segment far too small: the frame is projected again into the exact layout (per-tile offsets from
+    # the counts of the overflowing pass)
     assert Rz._predictor.last_tile[key] > 32
     Rz._predictor.last_tile[key] = -100  # predicts the minimum...
     old = Rz.round_tile_capacity
     Rz.round_tile_capacity = lambda n: 32 if n <= 56 else old(n)  # ...which this makes 32 slots
+    before = Rz.stats["reprojected"]
     try:
         d = _render(sc, device)
     finally:
         Rz.round_tile_capacity = old
+    assert Rz.stats["reprojected"] == before + 1
     for x, y in zip(a, d):
+        assert torch.equal(x, y)
+    # ... and the same route taken by policy: uniform segments judged wasteful (a few very dense tiles)
+    floor = Rz.UNIFORM_BYTES_FLOOR
+    Rz.UNIFORM_BYTES_FLOOR = 0
+    Rz._predictor.last_tile[key] = 1 << 20
+    try:
+        e = _render(sc, device)
+    finally:
+        Rz.UNIFORM_BYTES_FLOOR = floor
+    assert Rz.stats["reprojected"] == before + 2
+    for x, y in zip(a, e):
         assert torch.equal(x, y)
 
 
