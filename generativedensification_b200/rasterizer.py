@@ -227,6 +227,38 @@ def drive_forward(key, mailbox: Mailbox, stream, project, render, tile_offsets, 
 stats = {"forwards": 0, "reprojected": 0, "rerendered": 0}
 
 
+_camera_cache = {}
+
+
+def _camera(settings, device):
+    """(bg, viewmatrix, projmatrix, campos) of a settings tuple as contiguous FP32 tensors on `device` plus their
+    device pointers, remembered per settings OBJECT (callers build one GaussianRasterizer per camera and call it many
+    times, lightning/renderer.py:106-126): the tensors' storage is read at launch time, so in-place updates are seen."""
+    e = _camera_cache.get(id(settings))
+    if e is not None and e[0] is settings and e[1] == device:
+        return e[2]
+    t = tuple(_f32c(x, device) for x in (settings.bg, settings.viewmatrix, settings.projmatrix, settings.campos))
+    cam = t + tuple(_ptr(x) for x in t)
+    if len(_camera_cache) > 512:
+        _camera_cache.clear()
+    _camera_cache[id(settings)] = (settings, device, cam)  # keeps `settings` alive: its id cannot be reused meanwhile
+    return cam
+
+
+_scratch_cache = {}
+
+
+def _scratch(device, stream, nbytes: int) -> torch.Tensor:
+    """Grow-only key scratch per (device, stream): it is dead once the frame's tile sort has run, and work on one
+    stream is ordered, so consecutive frames of a stream share it (a fresh torch.empty of ~100 MB per frame otherwise)."""
+    k = (device.index, stream.cuda_stream)
+    t = _scratch_cache.get(k)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _scratch_cache[k] = t
+    return t
+
+
 class _ForwardState:
     """Opaque state kept between forward and backward (the reference keeps three byte tensors)."""
     __slots__ = ("geom", "img", "stream_buf", "capacity", "num_rendered", "P", "M")
@@ -264,10 +296,7 @@ def _forward_impl(settings: GaussianRasterizationSettings, means3D, sh, colors_p
         scales = _f32c(scales, device)
         rotations = _f32c(rotations, device)
         cov3Ds_precomp = _f32c(cov3Ds_precomp, device)
-        bg = _f32c(settings.bg, device)
-        view = _f32c(settings.viewmatrix, device)
-        proj = _f32c(settings.projmatrix, device)
-        campos = _f32c(settings.campos, device)
+        bg, view, proj, campos, bg_p, view_p, proj_p, campos_p = _camera(settings, device)
         stream = torch.cuda.current_stream(device)
         sptr = C.c_void_p(stream.cuda_stream)
 
@@ -285,11 +314,11 @@ def _forward_impl(settings: GaussianRasterizationSettings, means3D, sh, colors_p
         def project(tile_capacity: int, offsets):
             nbytes = (_lib.query_bytes("gdr_sort_scratch_bytes", W, H, tile_capacity) if offsets is None else
                       _lib.query_bytes("gdr_sort_scratch_exact_bytes", tile_capacity))
-            scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            scratch = _scratch(device, stream, nbytes)
             _lib.check(lib.gdr_forward_project(
                 P, int(settings.sh_degree), st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp),
                 _ptr(opacities), _ptr(scales), float(settings.scale_modifier), _ptr(rotations), _ptr(cov3Ds_precomp),
-                _ptr(view), _ptr(proj), _ptr(campos), float(settings.tanfovx), float(settings.tanfovy),
+                view_p, proj_p, campos_p, float(settings.tanfovx), float(settings.tanfovy),
                 int(bool(settings.prefiltered)), radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(),
                 scratch.data_ptr(), tile_capacity, _ptr(offsets), mailbox.ptr, flags, sptr), "gdr_forward_project")
             return scratch
@@ -299,7 +328,7 @@ def _forward_impl(settings: GaussianRasterizationSettings, means3D, sh, colors_p
             st.stream_buf = torch.empty(_lib.query_bytes("gdr_splat_stream_bytes", capacity), dtype=torch.uint8,
                                         device=device)
             _lib.check(lib.gdr_forward_render(
-                P, W, H, _ptr(bg), st.geom.data_ptr(), st.img.data_ptr(), st.stream_buf.data_ptr(),
+                P, W, H, bg_p, st.geom.data_ptr(), st.img.data_ptr(), st.stream_buf.data_ptr(),
                 scratch.data_ptr(), tile_capacity, _ptr(offsets), capacity, color.data_ptr(), depth.data_ptr(),
                 alpha.data_ptr(), flags | (_lib.FLAG_RERUN if rerun else 0), sptr), "gdr_forward_render")
 
@@ -358,18 +387,15 @@ def _backward_impl(settings, st: _ForwardState, saved, grad_color, grad_depth, g
     if mask == 0:
         return out
     with torch.cuda.device(device):
-        bg = _f32c(settings.bg, device)
-        view = _f32c(settings.viewmatrix, device)
-        proj = _f32c(settings.projmatrix, device)
-        campos = _f32c(settings.campos, device)
+        bg, view, proj, campos, bg_p, view_p, proj_p, campos_p = _camera(settings, device)
         grad_color = _f32c(grad_color, device)
         grad_depth = None if grad_depth is None else _f32c(grad_depth, device)
         grad_alpha = None if grad_alpha is None else _f32c(grad_alpha, device)
         scratch = torch.empty(_lib.query_bytes("gdr_backward_scratch_bytes", P), dtype=torch.uint8, device=device)
         sptr = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         _lib.check(lib.gdr_backward(
-            P, int(settings.sh_degree), M, W, H, _ptr(bg), _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(scales),
-            float(settings.scale_modifier), _ptr(rotations), _ptr(cov3Ds_precomp), _ptr(view), _ptr(proj), _ptr(campos),
+            P, int(settings.sh_degree), M, W, H, bg_p, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(scales),
+            float(settings.scale_modifier), _ptr(rotations), _ptr(cov3Ds_precomp), view_p, proj_p, campos_p,
             float(settings.tanfovx), float(settings.tanfovy), radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(),
             _ptr(st.stream_buf), st.capacity, alpha.data_ptr(), grad_color.data_ptr(), _ptr(grad_depth),
             _ptr(grad_alpha), scratch.data_ptr(), mask, _ptr(out["means2D"]), _ptr(out["colors"]),
