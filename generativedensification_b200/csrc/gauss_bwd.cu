@@ -343,8 +343,11 @@ __device__ __forceinline__ void gauss_backward_one(const GaussBackwardArgs& a, c
 
 // ACC = false stores every requested output row; ACC = true adds to it (views 1.. of a batch launch in
 // stream order after view 0, so the per-Gaussian gradients are summed over views deterministically).
+#ifndef GDR_GB_MINB
+#define GDR_GB_MINB 1
+#endif
 template <bool ACC>
-__global__ void __launch_bounds__(GB_THREADS) gauss_backward_kernel(const GaussBackwardArgs a) {
+__global__ void __launch_bounds__(GB_THREADS, GDR_GB_MINB) gauss_backward_kernel(const GaussBackwardArgs a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar;
     Rows rows;

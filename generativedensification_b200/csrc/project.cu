@@ -142,7 +142,10 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, float3 pos, float3 campos, 
     return make_float3(res[0], res[1], res[2]);
 }
 
-__global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjectArgs a) {
+#ifndef GDR_PROJ_MINB
+#define GDR_PROJ_MINB 1
+#endif
+__global__ void __launch_bounds__(PROJ_THREADS, GDR_PROJ_MINB) project_kernel(const ProjectArgs a) {
     extern __shared__ __align__(128) float smem[];
     const int v = blockIdx.y;  // view of the batch
     const float* __restrict__ viewmatrix = a.vw.view + (size_t)v * a.vw.cam_stride;
