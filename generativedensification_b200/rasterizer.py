@@ -107,11 +107,17 @@ class _CapacityPredictor:
 
     def predict_tile(self, key) -> int:
         m = self.last_tile.get(key)
-        return self.DEFAULT_TILE_CAPACITY if m is None else round_tile_capacity(2 * m + 256)
+        if m is None:
+            return self.DEFAULT_TILE_CAPACITY
+        return round_tile_capacity(int(TILE_HEADROOM * m) + 256)
 
     def update(self, key, r: int, max_tile: int = 0) -> None:
         self.last[key] = r
         self.last_tile[key] = max_tile
+
+
+# head-room of the per-tile key segments over the previous frame's densest tile (an overflow costs a second projection)
+TILE_HEADROOM = float(os.environ.get("GDR_TILE_HEADROOM", "2.0"))
 
 
 def round_tile_capacity(n: int) -> int:

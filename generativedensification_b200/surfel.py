@@ -35,7 +35,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .rasterizer import _f32c, _mailbox, _ptr, drive_forward
+from .rasterizer import _f32c, _mailbox, _ptr, _scratch, drive_forward
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -105,7 +105,7 @@ def _forward_impl(settings, means3D, sh, colors_precomp, opacities, scales, rota
         def project(tile_capacity: int, offsets):
             nbytes = (_lib.query_bytes("gdr_sort_scratch_bytes", W, H, tile_capacity) if offsets is None else
                       _lib.query_bytes("gdr_sort_scratch_exact_bytes", tile_capacity))
-            scratch = torch.empty(nbytes, **u8)
+            scratch = _scratch(device, stream, nbytes)
             _lib.check(lib.gdr_surfel_forward_project(
                 P, int(settings.sh_degree), st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp),
                 _ptr(opacities), _ptr(scales), st.scale_stride, float(settings.scale_modifier), _ptr(rotations),

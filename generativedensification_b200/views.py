@@ -25,8 +25,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .rasterizer import (PREFILTERED_MESSAGE, GaussianRasterizationSettings, _f32c, _mailbox, _ptr, drive_forward,
-                         options)
+from .rasterizer import (PREFILTERED_MESSAGE, GaussianRasterizationSettings, _f32c, _mailbox, _ptr, _scratch,
+                         drive_forward, options)
 
 
 class CameraBatch:
@@ -120,7 +120,7 @@ def _forward_views(cb: CameraBatch, means3D, sh, colors_precomp, opacities, scal
         def project(tile_capacity: int, offsets):
             nbytes = (one_view("gdr_sort_scratch_bytes", W, H, tile_capacity) if offsets is None else
                       one_view("gdr_sort_scratch_exact_bytes", tile_capacity))
-            scratch = torch.empty(V * nbytes, dtype=torch.uint8, device=device)
+            scratch = _scratch(device, stream, V * nbytes)  # grow-only per (device, stream): no GB-sized reallocation
             _lib.check(lib.gdr_views_forward_project(
                 V, P, cb.sh_degree, st.M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
                 _ptr(scales), cb.scale_modifier, _ptr(rotations), _ptr(cov3Ds_precomp), cb.cams.data_ptr(),

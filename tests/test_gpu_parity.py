@@ -458,3 +458,52 @@ def test_config4_densify_select_vs_reference(device):
     ref_sel = densify.select_top_k(ref_grad, K)
     overlap = int((sel & ref_sel).sum()) / K
     assert overlap >= 0.999  # only near-ties at the K-th value may differ (float-atomic summation order)
+
+
+def test_prefiltered_violation_raises(device):
+    """prefiltered=True promises that every Gaussian passes the near-plane test; the reference printf()s and traps on
+    the device when one does not (auxiliary.h:154-158).  Here the projection kernel flags it, the flag travels back with
+    the instance counts, and the call raises -- the CUDA context survives."""
+    from generativedensification_b200 import synthetic as S
+    from generativedensification_b200.rasterizer import PREFILTERED_MESSAGE, GaussianRasterizer
+
+    sc = SC._scene("prefiltered", 500, 64, 64, 21)
+    settings = S.settings_for(sc["camera"], sc["bg"], sc["sh_degree"], device)._replace(prefiltered=True)
+    t = {k: sc[k].to(device) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    m2 = torch.zeros(500, 4, device=device)
+    GaussianRasterizer(settings)(means3D=t["means3D"], means2D=m2, opacities=t["opacities"], shs=t["shs"],
+                                 scales=t["scales"], rotations=t["rotations"])  # everything in front: fine
+    behind = t["means3D"].clone()
+    cam_pos = torch.linalg.inv(sc["camera"]["world_view_transform"].T)[:3, 3].to(device)  # the true camera position
+    behind[7] = cam_pos  # view depth 0 <= 0.2
+    with pytest.raises(RuntimeError, match="prefiltered"):
+        GaussianRasterizer(settings)(means3D=behind, means2D=m2, opacities=t["opacities"], shs=t["shs"],
+                                     scales=t["scales"], rotations=t["rotations"])
+    assert PREFILTERED_MESSAGE.startswith("Point is filtered")
+    # the context is intact and the non-prefiltered call simply culls that Gaussian
+    out = GaussianRasterizer(settings._replace(prefiltered=False))(
+        means3D=behind, means2D=m2, opacities=t["opacities"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+    assert int(out[1][7]) == 0 and bool(torch.isfinite(out[0]).all())
+
+
+def test_nan_mean_follows_the_reference(device):
+    """The reference's near-plane test is `p_view.z <= 0.2 -> cull` (auxiliary.h:152): a NaN depth PASSES it, the
+    Gaussian then ends with an empty tile rectangle (radius 0, no contribution), and markVisible reports it visible."""
+    from generativedensification_b200 import synthetic as S
+    from generativedensification_b200.rasterizer import GaussianRasterizer
+
+    sc = SC._scene("nan", 300, 48, 48, 22)
+    settings = S.settings_for(sc["camera"], sc["bg"], sc["sh_degree"], device)
+    t = {k: sc[k].to(device) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    bad = t["means3D"].clone()
+    bad[5] = float("nan")
+    m2 = torch.zeros(300, 4, device=device)
+    rast = GaussianRasterizer(settings)
+    clean = rast(means3D=t["means3D"], means2D=m2, opacities=t["opacities"] * (torch.arange(300, device=device) != 5)[:, None],
+                 shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+    out = rast(means3D=bad, means2D=m2, opacities=t["opacities"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+    assert int(out[1][5]) == 0
+    for a, b in zip((out[0], out[2], out[3]), (clean[0], clean[2], clean[3])):
+        assert torch.equal(a, b)  # the image is the scene without that Gaussian: no NaN leaks in
+    vis = rast.markVisible(bad)
+    assert bool(vis[5])  # NaN <= 0.2 is false: "visible", as in the reference
