@@ -11,6 +11,8 @@
 //                       boolean mask and the two compacted index lists (ascending), all on the device:
 //                       no sort, no host round trip.  Ties at the threshold go to the lowest indices
 //                       (torch.topk leaves the choice among equal values unspecified).
+#include <cooperative_groups.h>
+
 #include "kernels.h"
 
 namespace gdr {
@@ -67,6 +69,7 @@ __global__ void score_kernel(int V, int P, const float* __restrict__ accum, cons
 }
 
 constexpr int SEL_THREADS = 1024;
+constexpr int SEL_CLUSTER = 8;  // CTAs (SMs) of the one cluster that selects; partial results travel through DSMEM
 
 // Order-preserving key of a candidate's score: 0 = not a candidate, NaN sorts above everything (as in torch.topk).
 __device__ __forceinline__ uint32_t score_key(float s) {
@@ -75,15 +78,53 @@ __device__ __forceinline__ uint32_t score_key(float s) {
     return __float_as_uint(s) + 1u;
 }
 
-// One CTA.  counts[0] = number selected, counts[1] = number of candidates not selected.
-__global__ void __launch_bounds__(SEL_THREADS)
+struct SelShared {
+    uint32_t hist[256];   // this CTA's histogram of the current digit
+    uint32_t counts[3];   // this CTA's range: candidates above the threshold, ties at it, candidates in total
+};
+
+constexpr int SEL_VEC = 4;                         // consecutive elements per thread and step (one 128-bit load)
+constexpr int SEL_STEP = SEL_THREADS * SEL_VEC;    // elements a CTA covers per step
+
+// keys of elements i .. i + 3 (0 beyond `end`); one LDG.128 when the row is whole and aligned
+__device__ __forceinline__ void load_keys(const float* __restrict__ score, bool aligned, int i, int end, uint32_t key[SEL_VEC]) {
+    if (aligned && i + SEL_VEC <= end) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(score + i));
+        key[0] = score_key(v.x);
+        key[1] = score_key(v.y);
+        key[2] = score_key(v.z);
+        key[3] = score_key(v.w);
+    } else {
+#pragma unroll
+        for (int j = 0; j < SEL_VEC; j++) key[j] = i + j < end ? score_key(__ldg(score + i + j)) : 0u;
+    }
+}
+
+// ONE thread-block cluster of SEL_CLUSTER CTAs (a single CTA sweeping P five times was fine at 262 144 candidates and
+// took ~1 ms at 2 M).  CTA r owns the contiguous index range [r * chunk, (r + 1) * chunk); a thread handles four
+// consecutive elements per step (one 128-bit load, and a quarter of the barriers of the ordered sweep).
+//   radix select   4 passes over the keys' bytes, most significant first: every CTA histograms its range, the cluster
+//                  barrier publishes the histograms, every CTA sums its peers' through distributed shared memory
+//                  (cluster.map_shared_rank) and picks the digit -- redundantly, from identical data;
+//   count          one sweep: per range the candidates above the threshold, the ties at it, the candidates in total --
+//                  exchanged the same way, which gives every CTA the number of ties / selected / rest before its range;
+//   write          one ordered sweep: the mask and the two ascending index lists at their final positions.
+// counts[0] = number selected, counts[1] = number of candidates not selected.
+__global__ void __cluster_dims__(SEL_CLUSTER, 1, 1) __launch_bounds__(SEL_THREADS)
 topk_select_kernel(int P, const float* __restrict__ score, int k, uint8_t* __restrict__ selected,
                    int32_t* __restrict__ selected_idx, int32_t* __restrict__ rest_idx, int32_t* __restrict__ counts) {
-    __shared__ uint32_t hist[256];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ SelShared sh;
+    __shared__ uint32_t total_hist[256];
     __shared__ uint32_t s_prefix, s_k;
     __shared__ uint32_t wsum[3][SEL_THREADS / 32];
     __shared__ uint32_t run[3];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int rank = (int)cluster.block_rank();
+    const int chunk = ((P + SEL_CLUSTER - 1) / SEL_CLUSTER + SEL_STEP - 1) / SEL_STEP * SEL_STEP;
+    const int i0 = min(P, rank * chunk), i1 = min(P, i0 + chunk);
+    const bool aligned = (((uintptr_t)score) & 15u) == 0;
 
     // ---- radix select: the key T of the k-th largest candidate and how many keys equal to T to take ----
     if (tid == 0) {
@@ -94,21 +135,31 @@ topk_select_kernel(int P, const float* __restrict__ score, int k, uint8_t* __res
     bool all = false;
     for (int pass = 0; pass < 4 && !all; pass++) {
         const int shift = 24 - 8 * pass;
-        if (tid < 256) hist[tid] = 0;
+        if (tid < 256) sh.hist[tid] = 0;
         __syncthreads();
         const uint32_t prefix = s_prefix, kk = s_k;
         const uint32_t hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-        for (int i = tid; i < P; i += SEL_THREADS) {
-            const uint32_t key = score_key(score[i]);
-            if (key != 0u && (key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        for (int base = i0; base < i1; base += SEL_STEP) {
+            uint32_t key[SEL_VEC];
+            load_keys(score, aligned, base + SEL_VEC * tid, i1, key);
+#pragma unroll
+            for (int j = 0; j < SEL_VEC; j++)
+                if (key[j] != 0u && (key[j] & hi_mask) == prefix) atomicAdd(&sh.hist[(key[j] >> shift) & 255u], 1u);
         }
-        __syncthreads();
-        if (tid == 0) {
+        cluster.sync();  // every CTA's histogram is complete and visible cluster-wide
+        if (tid < 256) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int r = 0; r < SEL_CLUSTER; r++) t += cluster.map_shared_rank(&sh, r)->hist[tid];
+            total_hist[tid] = t;
+        }
+        cluster.sync();  // peers have read this CTA's histogram: it may be cleared for the next pass
+        if (tid == 0) {  // the same decision in every CTA (identical totals)
             uint32_t acc = 0;
             int b = 255;
             for (; b >= 0; b--) {
-                if (acc + hist[b] >= kk) break;
-                acc += hist[b];
+                if (acc + total_hist[b] >= kk) break;
+                acc += total_hist[b];
             }
             if (b < 0) {  // fewer candidates than k (only possible in pass 0): take them all
                 s_k = 0xffffffffu;
@@ -127,58 +178,115 @@ topk_select_kernel(int P, const float* __restrict__ score, int k, uint8_t* __res
         threshold = 0xffffffffu;
         need_ties = 0;
     }
-    if (tid < 3) run[tid] = 0;
+    const bool take_all = need_ties == 0xffffffffu;
+
+    // ---- count: this range's candidates above the threshold / at it / in total ----
+    if (tid < 3) sh.counts[tid] = 0;
+    __syncthreads();
+    {
+        uint32_t n_above = 0, n_tie = 0, n_cand = 0;
+        for (int base = i0; base < i1; base += SEL_STEP) {
+            uint32_t key[SEL_VEC];
+            load_keys(score, aligned, base + SEL_VEC * tid, i1, key);
+#pragma unroll
+            for (int j = 0; j < SEL_VEC; j++) {
+                const bool cand = key[j] != 0u;
+                n_cand += cand;
+                n_above += cand && (take_all || key[j] > threshold);
+                n_tie += cand && !take_all && key[j] == threshold;
+            }
+        }
+        n_above = __reduce_add_sync(0xffffffffu, n_above);
+        n_tie = __reduce_add_sync(0xffffffffu, n_tie);
+        n_cand = __reduce_add_sync(0xffffffffu, n_cand);
+        if (lane == 0) {
+            atomicAdd(&sh.counts[0], n_above);
+            atomicAdd(&sh.counts[1], n_tie);
+            atomicAdd(&sh.counts[2], n_cand);
+        }
+    }
+    cluster.sync();
+    if (tid == 0) {  // what lies before this range, in index order
+        uint32_t ties_before = 0, sel_before = 0, rest_before = 0, sel_total = 0, rest_total = 0;
+        for (int r = 0; r < SEL_CLUSTER; r++) {
+            const SelShared* peer = cluster.map_shared_rank(&sh, r);
+            const uint32_t above = peer->counts[0], tie = peer->counts[1], cand = peer->counts[2];
+            // ties are taken in index order until need_ties of them are selected
+            const uint32_t tie_taken = take_all ? 0u : min(tie, need_ties - min(need_ties, ties_before));
+            const uint32_t sel = above + tie_taken;
+            if (r < rank) {
+                sel_before += sel;
+                rest_before += cand - sel;
+            }
+            if (r == rank) run[0] = ties_before;  // ties before this CTA's first element
+            ties_before += tie;
+            sel_total += sel;
+            rest_total += cand - sel;
+        }
+        run[1] = sel_before;
+        run[2] = rest_before;
+        if (rank == 0 && counts) {
+            counts[0] = (int32_t)sel_total;
+            counts[1] = (int32_t)rest_total;
+        }
+    }
     __syncthreads();
 
-    // ---- one ordered sweep: mask + the two compacted index lists ----
-    for (int base = 0; base < P; base += SEL_THREADS) {
-        const int i = base + tid;
-        const uint32_t key = i < P ? score_key(score[i]) : 0u;
-        const bool cand = key != 0u;
-        const bool tie = cand && key == threshold && need_ties != 0xffffffffu;
-        const bool above = cand && (need_ties == 0xffffffffu ? true : key > threshold);
-        // block-exclusive ranks of (tie) in index order
-        const unsigned bt = __ballot_sync(0xffffffffu, tie);
-        if (lane == 0) wsum[0][wid] = __popc(bt);
+    // ---- one ordered sweep over this range: mask + the two compacted index lists ----
+    // block-exclusive prefix of a per-thread count, in thread (= index) order; `slot` selects the scratch row
+    auto block_excl = [&](uint32_t mine, int slot) {
+        const uint32_t incl = (uint32_t)warp_incl_scan((int)mine);
+        if (lane == 31) wsum[slot][wid] = incl;
         __syncthreads();
-        uint32_t tie_rank = run[0] + __popc(bt & ((1u << lane) - 1u));
-        for (int w = 0; w < wid; w++) tie_rank += wsum[0][w];
-        const bool sel = above || (tie && tie_rank < need_ties);
-        const bool rest = cand && !sel;
-        const unsigned bs = __ballot_sync(0xffffffffu, sel), br = __ballot_sync(0xffffffffu, rest);
-        if (lane == 0) {
-            wsum[1][wid] = __popc(bs);
-            wsum[2][wid] = __popc(br);
+        uint32_t before = incl - mine;
+        for (int w = 0; w < wid; w++) before += wsum[slot][w];
+        return before;
+    };
+    for (int base = i0; base < i1; base += SEL_STEP) {
+        const int i = base + SEL_VEC * tid;
+        uint32_t key[SEL_VEC];
+        load_keys(score, aligned, i, i1, key);
+        bool cand[SEL_VEC], tie[SEL_VEC], sel[SEL_VEC];
+        uint32_t n_tie = 0;
+#pragma unroll
+        for (int j = 0; j < SEL_VEC; j++) {
+            cand[j] = key[j] != 0u;
+            tie[j] = cand[j] && key[j] == threshold && !take_all;
+            n_tie += tie[j];
         }
-        __syncthreads();
-        uint32_t ps = run[1] + __popc(bs & ((1u << lane) - 1u)), pr = run[2] + __popc(br & ((1u << lane) - 1u));
-        for (int w = 0; w < wid; w++) {
-            ps += wsum[1][w];
-            pr += wsum[2][w];
+        uint32_t tie_rank = run[0] + block_excl(n_tie, 0);
+        uint32_t n_sel = 0, n_rest = 0;
+#pragma unroll
+        for (int j = 0; j < SEL_VEC; j++) {
+            const bool above = cand[j] && (take_all ? true : key[j] > threshold);
+            sel[j] = above || (tie[j] && tie_rank < need_ties);
+            tie_rank += tie[j];
+            n_sel += sel[j];
+            n_rest += cand[j] && !sel[j];
         }
-        if (i < P) {
-            if (selected) selected[i] = sel ? 1 : 0;
-            if (sel && selected_idx) selected_idx[ps] = i;
-            if (rest && rest_idx) rest_idx[pr] = i;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t t0 = 0, t1 = 0, t2 = 0;
-            for (int w = 0; w < SEL_THREADS / 32; w++) {
-                t0 += wsum[0][w];
-                t1 += wsum[1][w];
-                t2 += wsum[2][w];
+        uint32_t ps = run[1] + block_excl(n_sel, 1), pr = run[2] + block_excl(n_rest, 2);
+#pragma unroll
+        for (int j = 0; j < SEL_VEC; j++) {
+            if (i + j < i1) {
+                if (selected) selected[i + j] = sel[j] ? 1 : 0;
+                if (sel[j]) {
+                    if (selected_idx) selected_idx[ps] = i + j;
+                    ps++;
+                } else if (cand[j]) {
+                    if (rest_idx) rest_idx[pr] = i + j;
+                    pr++;
+                }
             }
-            run[0] += t0;
-            run[1] += t1;
-            run[2] += t2;
+        }
+        __syncthreads();  // every thread has read run[] and wsum[]
+        if (tid == SEL_THREADS - 1) {  // the last thread's inclusive totals close the step
+            run[0] = tie_rank;
+            run[1] = ps;
+            run[2] = pr;
         }
         __syncthreads();
     }
-    if (tid == 0 && counts) {
-        counts[0] = (int32_t)run[1];
-        counts[1] = (int32_t)run[2];
-    }
+    cluster.sync();  // no CTA leaves while a peer may still read its shared memory
 }
 
 }  // namespace
@@ -205,7 +313,7 @@ cudaError_t launch_densify_score(int V, int P, const float* accum, const uint8_t
 
 cudaError_t launch_topk_select(int P, const float* score, int k, uint8_t* selected, int32_t* selected_idx,
                                int32_t* rest_idx, int32_t* counts, cudaStream_t s) {
-    topk_select_kernel<<<1, SEL_THREADS, 0, s>>>(P, score, k, selected, selected_idx, rest_idx, counts);
+    topk_select_kernel<<<SEL_CLUSTER, SEL_THREADS, 0, s>>>(P, score, k, selected, selected_idx, rest_idx, counts);
     return cudaGetLastError();
 }
 

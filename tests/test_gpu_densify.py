@@ -103,3 +103,27 @@ def test_mse_grad_matches_autograd(device):
                "gdr_mse_grad")
     assert torch.allclose(g, g_ref, rtol=1e-6, atol=1e-12)
     assert abs(float(l) - float(loss.detach())) <= 1e-6 * float(loss.detach())
+
+
+def test_topk_device_at_two_million_candidates(device):
+    """The cluster radix select (8 CTAs exchanging histograms through distributed shared memory) at the stress size:
+    exact against torch.topk, ties resolved to the lowest indices, index lists ascending and complete."""
+    P, k = 2_000_000, 123_457
+    gen = torch.Generator().manual_seed(9)
+    scores = torch.rand(P, generator=gen)
+    scores[torch.randint(0, P, (P // 10,), generator=gen)] = -1.0     # not candidates
+    scores[torch.randint(0, P, (P // 20,), generator=gen)] = 0.5      # a big tie class ...
+    scores = scores.to(device)
+    kth = torch.topk(scores, k).values[-1]
+    sel, sel_idx, rest_idx, counts = D.top_k_device(scores, k)
+    c = counts.cpu().numpy()
+    n_cand = int((scores >= 0).sum())
+    assert c[0] == k and c[1] == n_cand - k
+    assert bool((scores[sel] >= kth).all()) and bool((scores[(scores >= 0) & ~sel] <= kth).all())
+    assert torch.equal(sel_idx[:c[0]].long(), torch.nonzero(sel).squeeze(-1))
+    assert torch.equal(rest_idx[:c[1]].long(), torch.nonzero((scores >= 0) & ~sel).squeeze(-1))
+    # ... cut in the middle: with the threshold inside the tie class, exactly the lowest-index ties are taken
+    k2 = int((scores > 0.5).sum()) + 1000
+    sel2, _, _, c2 = D.top_k_device(scores, k2)
+    ties = torch.nonzero(scores == 0.5).squeeze(-1)
+    assert int(c2[0]) == k2 and bool(sel2[ties[:1000]].all()) and not bool(sel2[ties[1000:]].any())
