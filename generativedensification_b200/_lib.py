@@ -103,8 +103,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if not os.path.isfile(path) or (os.path.isfile(_build.NVCC) and not _build.is_fresh()):
+    path = os.environ.get("GDR_LIB")  # experiments: a pre-built variant of the library, loaded as it is
+    if path:
+        if not os.path.isfile(path):
+            raise GdrError(f"GDR_LIB={path} does not exist")
+    else:
+        path = _build.LIB
+    if path == _build.LIB and (not os.path.isfile(path) or (os.path.isfile(_build.NVCC) and not _build.is_fresh())):
         try:
             _build.build()
         except Exception as e:  # no nvcc, or a compile error: fail loudly
