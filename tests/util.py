@@ -170,7 +170,7 @@ GRAD_ELEM_ATOL = 1e-6  # times max |ref|
 GRAD_ELEM_FRAC = 1e-3
 
 
-def assert_grad_close(ours, ref, name="grad", tol=GRAD_TOL, elem_rtol=GRAD_ELEM_RTOL):
+def assert_grad_close(ours, ref, name="grad", tol=GRAD_TOL, elem_rtol=GRAD_ELEM_RTOL, elem_atol=GRAD_ELEM_ATOL):
     """Assert both bounds above; accepts numpy arrays or tensors.  Returns (norm-relative error, worst per-element
     relative error over the selected elements)."""
     to_np = lambda t: t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
@@ -185,7 +185,7 @@ def assert_grad_close(ours, ref, name="grad", tol=GRAD_TOL, elem_rtol=GRAD_ELEM_
     assert e_inf <= tol, (name, "norm-relative", e_inf)
     big = np.abs(ref) > max(1e-6, GRAD_ELEM_FRAC * scale)
     rel = float((err[big] / np.abs(ref)[big]).max()) if big.any() else 0.0
-    bad = err[big] > elem_rtol * np.abs(ref)[big] + GRAD_ELEM_ATOL * scale
+    bad = err[big] > elem_rtol * np.abs(ref)[big] + elem_atol * scale
     assert not bad.any(), (name, "per-element relative", rel, int(bad.sum()))
     return e_inf, rel
 
