@@ -29,6 +29,7 @@ tensors:
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 from typing import NamedTuple, Optional
@@ -37,6 +38,9 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+
+
+_NULL_CONTEXT = contextlib.nullcontext()
 
 
 def cpu_deep_copy_tuple(input_tuple):
@@ -66,6 +70,11 @@ def _ptr(t: Optional[torch.Tensor]):
     if t is None or t.numel() == 0:
         return None
     return t.data_ptr()
+
+
+def _on_device(device):
+    """Context that makes `device` current; free when it already is (torch.cuda.device costs ~4 us per use)."""
+    return _NULL_CONTEXT if torch.cuda.current_device() == device.index else torch.cuda.device(device)
 
 
 def _f32c(t: torch.Tensor, device) -> torch.Tensor:
@@ -294,7 +303,7 @@ def _forward_impl(settings: GaussianRasterizationSettings, means3D, sh, colors_p
         z = torch.zeros
         return z(3, H, W, **f32), radii, z(1, H, W, **f32), z(1, H, W, **f32), st
 
-    with torch.cuda.device(device):
+    with _on_device(device):
         means3D = _f32c(means3D, device)
         sh = _f32c(sh, device)
         colors_precomp = _f32c(colors_precomp, device)
@@ -392,7 +401,7 @@ def _backward_impl(settings, st: _ForwardState, saved, grad_color, grad_depth, g
         out["cov3D"] = torch.empty(P, 6, **f32)
     if mask == 0:
         return out
-    with torch.cuda.device(device):
+    with _on_device(device):
         bg, view, proj, campos, bg_p, view_p, proj_p, campos_p = _camera(settings, device)
         grad_color = _f32c(grad_color, device)
         grad_depth = None if grad_depth is None else _f32c(grad_depth, device)
@@ -415,27 +424,40 @@ def _backward_impl(settings, st: _ForwardState, saved, grad_color, grad_depth, g
 # ------------------------------------------------------------------------------
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         raster_settings):
+    if not (torch.is_grad_enabled() and (means3D.requires_grad or means2D.requires_grad or sh.requires_grad or
+                                         colors_precomp.requires_grad or opacities.requires_grad or
+                                         scales.requires_grad or rotations.requires_grad or
+                                         cov3Ds_precomp.requires_grad)):
+        # nothing to differentiate (the eval loops run under no_grad, lightning/network.py:827-838): same outputs
+        # without the autograd.Function round trip, and the frame's state is released right away
+        return _forward_checked(raster_settings, (means3D, sh, colors_precomp, opacities, scales, rotations,
+                                                  cov3Ds_precomp))[:4]
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                                      cov3Ds_precomp, raster_settings)
+
+
+def _forward_checked(raster_settings, args):
+    """_forward_impl with the reference's debug behaviour (__init__.py:63-78): on failure the inputs are dumped."""
+    if not raster_settings.debug:
+        return _forward_impl(raster_settings, *args)
+    cpu_args = cpu_deep_copy_tuple((raster_settings.bg, *args, raster_settings.viewmatrix,
+                                    raster_settings.projmatrix, raster_settings.campos))
+    try:
+        out = _forward_impl(raster_settings, *args)
+        torch.cuda.synchronize(args[0].device)  # debug mode surfaces CUDA errors here (auxiliary.h:166-173)
+    except Exception as ex:
+        torch.save(cpu_args, "snapshot_fw.dump")
+        print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+        raise ex
+    return out
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                 raster_settings):
-        args = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
-        if raster_settings.debug:
-            cpu_args = cpu_deep_copy_tuple((raster_settings.bg, *args, raster_settings.viewmatrix,
-                                            raster_settings.projmatrix, raster_settings.campos))
-            try:
-                color, radii, depth, alpha, st = _forward_impl(raster_settings, *args)
-                torch.cuda.synchronize(means3D.device)  # debug mode surfaces CUDA errors here (auxiliary.h:166-173)
-            except Exception as ex:
-                torch.save(cpu_args, "snapshot_fw.dump")
-                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
-                raise ex
-        else:
-            color, radii, depth, alpha, st = _forward_impl(raster_settings, *args)
+        color, radii, depth, alpha, st = _forward_checked(
+            raster_settings, (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
 
         ctx.raster_settings = raster_settings
         ctx.num_rendered = st.num_rendered
