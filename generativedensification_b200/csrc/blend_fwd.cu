@@ -23,10 +23,10 @@
 //     the stream copy), and every warp walks only the records whose bit is set for
 //     its region (ballot + find-first-set).  Records that cannot reach alpha = 1/255 anywhere
 //     in a warp's region cost that warp nothing;
-//   * for the pairs that are evaluated, a per-record conservative threshold on the
-//     exponent skips the expf when alpha cannot reach 1/255 (exact: the slack is far
-//     larger than any rounding error; everything near the cut takes the reference's
-//     exact test).
+//   * every pair of a visited record takes the reference's exact test (full-precision expf as a packed
+//     bit-exact replica, common.cuh: expf2); a pixel that does not blend a record carries alpha = 0
+//     through the updates, which makes them the exact identity -- no divergent branch inside a visit;
+//   * optional fused epilogue of Renderer.render_img (clamped HWC image, clamp mask parked in n_contrib).
 #include "kernels.h"
 #include "tile_iter.cuh"
 
