@@ -7,8 +7,9 @@
 // tiles_touched, the blocking read-back of the instance count and
 // duplicateWithKeys (rasterizer_impl.cu:278-301, 70-111).  Differences in
 // structure, not in values:
-//   * inputs with a 12-byte stride (means, scales, SH rows) are staged through
-//     shared memory with coalesced 128-bit loads;
+//   * inputs with a 12-byte stride (means, scales, SH rows) reach shared memory as whole-CTA
+//     slices moved by the bulk-copy engine (cp.async.bulk + mbarrier; one thread issues every
+//     slice), and the 48-byte records / 24-byte covariances leave the same way;
 //   * the outputs of the blend are written as one packed 48-byte Splat record;
 //   * the same launch bins the instances: every (Gaussian, tile) pair that
 //     survives the exact culling test claims a slot of its tile's key segment with

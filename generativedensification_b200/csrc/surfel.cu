@@ -3,8 +3,8 @@
 // Serves the `diff_surfel_rasterization`-shaped module that lightning/renderer_2dgs.py:7-10,224-233
 // of the reference imports.  PARITY UNPINNED: that extension's source is not in the reference tree
 // (SURVEY.md 8c / 8f-3), so the arithmetic follows the published 2DGS algorithm and is checked against
-// oracle/surfel_oracle.py (dense torch restatement, autograd backward).  Binning (tile scan, emit,
-// per-tile sort + record gather) is shared with the 3DGS path (binning.cu); the stream records are the
+// oracle/surfel_oracle.py (dense torch restatement, autograd backward).  Binning (slot claims inside the
+// projection kernel, tile_iter.cuh; per-tile sort + record gather, binning.cu) is shared with the 3DGS path; the stream records are the
 // 80-byte Surfel of surfel.cuh, staged per tile with cp.async.bulk like the 48-byte Splat stream.
 #include "kernels.h"
 #include "sh.cuh"
