@@ -610,7 +610,10 @@ def main():
                     gpu_launches=(3 + (0 if a.forward_only else 2)) * len(cams) * a.steps,
                     roofline={"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                               "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": measured_traffic(dominant, a),
-                              "peak_source": f"of {peak_kind}", "ms_per_launch": dom_ms,
+                              "peak_source": ("MEASURED_PEAKS.json hbm_gbs (driver-measured copy bandwidth of this pool's B200s)"
+                                              if peak_kind == "measured" else
+                                              "fallback of /opt/skills/guides/B200_PROFILING.md (no MEASURED_PEAKS.json)"),
+                              "ms_per_launch": dom_ms,
                               "algorithmic_bytes_per_launch": alg[dominant],
                               "note": "blend kernels are FP32-issue/atomic bound, not HBM bound (SURVEY 7.3.1)"},
                     pipeline={"algorithmic_bytes_per_view": B_f + B_b, "achieved": pipe_achieved, "unit": "GB/s",
