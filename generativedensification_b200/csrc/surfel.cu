@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(SP_THREADS) surfel_project_kernel(const Surfel
             const float3 p = make_float3(__ldg(a.means3D + 3 * (size_t)idx), __ldg(a.means3D + 3 * (size_t)idx + 1),
                                          __ldg(a.means3D + 3 * (size_t)idx + 2));
             const float3 pv = xform_point_4x3(p, a.view);
-            if (pv.z > SURFEL_NEAR) {
+            if (!(pv.z <= SURFEL_NEAR)) {  // the near-plane test of in_frustum: a NaN depth passes, as in the 3DGS path
                 float Tu[3], Tv[3], Tw[3];
                 float3 normal;
                 if (a.transmat_precomp) {

@@ -257,3 +257,18 @@ def test_capacity_misprediction_and_side_stream(device):
         assert torch.equal(a["radii"], other["radii"])
         # float atomics: summation order differs from run to run
         assert SU.rel_err(other["grad_means3D"], a["grad_means3D"]) <= 1e-5
+
+
+def test_nan_mean_is_not_silently_dropped(device):
+    """The near-plane test is `!(z <= near)` as in the reference family's in_frustum: a NaN mean passes it (the 3DGS
+    path: tests/test_gpu_parity.py::test_nan_mean_follows_the_reference).  The render must complete, and the other
+    surfels' pixels must not change where the NaN one does not reach."""
+    sc = dict(SCENES["s_deg0"])
+    clean = SU.run_ours(sc, device)
+    sc["means3D"] = sc["means3D"].clone()
+    sc["means3D"][0] = float("nan")
+    bad = SU.run_ours(sc, device, grads=SU.surfel_upstream(sc))
+    torch.cuda.synchronize(device)
+    assert bad["color"].shape == clean["color"].shape
+    finite = torch.isfinite(bad["color"]).all(0)
+    assert float(finite.float().mean()) > 0.5  # the NaN surfel's footprint is bounded by the tile clamp
