@@ -18,6 +18,7 @@
 // Compared with a global 64-bit radix sort of all R pairs (6+ passes over 12 B/pair) plus a
 // prefix sum and a duplication pass, each instance is written once as an 8-byte key and read once.
 #include "kernels.h"
+#include "surfel.cuh"
 #include "tile_iter.cuh"
 
 namespace gdr {
@@ -387,6 +388,10 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
             const float tx0 = (float)((tile % gx) * TILE), ty0 = (float)((tile / gx) * TILE);
             const unsigned m = region_mask4(w[0].x - tx0, w[0].y - ty0, w[1].x, w[1].y, w[1].z, w[0].z);
             w[0].w = __uint_as_float(__float_as_uint(w[0].w) | (m << STREAM_REGION_SHIFT));
+        } else {
+            // the surfel path's eight 8x4 blocks (surfel.cuh): the bits replace the reach in the stream copy's r4.w
+            const float tx0 = (float)((tile % gx) * TILE), ty0 = (float)((tile / gx) * TILE);
+            w[4].w = __uint_as_float(surfel_region_mask8(w[0], w[1], w[2], w[3], tx0, ty0));
         }
         float4* dst4 = out + (size_t)i * RQ;
 #pragma unroll

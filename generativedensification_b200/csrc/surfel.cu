@@ -6,6 +6,8 @@
 // oracle/surfel_oracle.py (dense torch restatement, autograd backward).  Binning (slot claims inside the
 // projection kernel, tile_iter.cuh; per-tile sort + record gather, binning.cu) is shared with the 3DGS path; the stream records are the
 // 80-byte Surfel of surfel.cuh, staged per tile with cp.async.bulk like the 48-byte Splat stream.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "sh.cuh"
 #include "surfel.cuh"
@@ -279,20 +281,15 @@ __device__ __forceinline__ bool surfel_pair(const Surfel& s, float px, float py,
     return !(e.alpha < ALPHA_MIN);
 }
 
-// Bit i of words[k] set iff record 32 k + i of the chunk can reach the warp's 8x4 pixel block (bx .. bx+7, by .. by+3).
-__device__ __forceinline__ void classify_chunk(const Surfel* sp, int cnt, int lane, float bx, float by,
+// Bit i of words[k] set iff record 32 k + i of the chunk can reach the warp's 8x4 pixel block: the block's bit of the
+// mask tile_sort left in the stream copy's r4.w (surfel_region_mask8, surfel.cuh).  all_blocks: ignore the masks
+// (GDR_SURFEL_MASKS=0; the tests compare the two modes bit for bit).
+__device__ __forceinline__ void classify_chunk(const Surfel* sp, int cnt, int lane, int warp, bool all_blocks,
                                                unsigned (&words)[SCHUNK / 32]) {
 #pragma unroll
     for (int k = 0; k < SCHUNK / 32; k++) {
-        bool hit = false;
         const int j = k * 32 + lane;
-        if (j < cnt) {
-            const float4 r0 = sp[j].r0;
-            const float reach = sp[j].r4.w;
-            const float ddx = r0.x - fminf(fmaxf(r0.x, bx), bx + 7.f);
-            const float ddy = r0.y - fminf(fmaxf(r0.y, by), by + 3.f);
-            hit = !(fabsf(ddx) > reach) && !(fabsf(ddy) > reach);
-        }
+        const bool hit = j < cnt && (all_blocks || ((__float_as_uint(sp[j].r4.w) >> warp) & 1u));
         words[k] = __ballot_sync(0xffffffffu, hit);
     }
 }
@@ -300,7 +297,7 @@ __device__ __forceinline__ void classify_chunk(const Surfel* sp, int cnt, int la
 __global__ void __launch_bounds__(SB_THREADS)
 surfel_blend_forward_kernel(int W, int H, int gx, int n_tiles_total, ImageState img, const Surfel* __restrict__ stream, int64_t capacity,
                             const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_allmap,
-                            float* __restrict__ aux) {
+                            float* __restrict__ aux, const int all_blocks) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SurfelSmem& sm = *reinterpret_cast<SurfelSmem*>(smem_raw);
     pdl_wait();  // launched as a programmatic dependent of tile_sort
@@ -314,7 +311,6 @@ surfel_blend_forward_kernel(int W, int H, int gx, int n_tiles_total, ImageState 
     const int py = tile_y * TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
-    const float bxf = (float)(tile_x * TILE + (warp & 1) * 8), byf = (float)(tile_y * TILE + (warp >> 1) * 4);
     if (threadIdx.x == 0) {
         mbar_init(&sm.full[0], 1);
         mbar_init(&sm.full[1], 1);
@@ -346,7 +342,7 @@ surfel_blend_forward_kernel(int W, int H, int gx, int n_tiles_total, ImageState 
         // continue: with them the lanes do not reconverge until the loop ends -- ncu showed 2 active threads per
         // instruction and a 15x slower kernel.)
         unsigned words[SCHUNK / 32];
-        classify_chunk(sp, cnt, lane, bxf, byf, words);
+        classify_chunk(sp, cnt, lane, warp, all_blocks != 0, words);
 #pragma unroll
         for (int k = 0; k < SCHUNK / 32; k++) {
             unsigned word = words[k];
@@ -430,7 +426,7 @@ __global__ void __launch_bounds__(SB_THREADS)
 surfel_blend_backward_kernel(int W, int H, int gx, int n_tiles_total, ImageState img, const Surfel* __restrict__ stream, int64_t capacity,
                              const float* __restrict__ bg, const float* __restrict__ out_allmap,
                              const float* __restrict__ aux, const float* __restrict__ dL_dcolor,
-                             const float* __restrict__ dL_dallmap, float* __restrict__ accum) {
+                             const float* __restrict__ dL_dallmap, float* __restrict__ accum, const int all_blocks) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SurfelSmem& sm = *reinterpret_cast<SurfelSmem*>(smem_raw);
     const int tile = tile_from_order(img.header, img.order, n_tiles_total, (int)blockIdx.x);
@@ -444,7 +440,6 @@ surfel_blend_backward_kernel(int W, int H, int gx, int n_tiles_total, ImageState
     const int py = tile_y * TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
-    const float bxf = (float)(tile_x * TILE + (warp & 1) * 8), byf = (float)(tile_y * TILE + (warp >> 1) * 4);
     const size_t HW = (size_t)H * W, pid = (size_t)py * W + px;
 
     const uint32_t last_contributor = inside ? img.n_contrib[pid] : 0u;
@@ -509,7 +504,7 @@ surfel_blend_backward_kernel(int W, int H, int gx, int n_tiles_total, ImageState
         int j_hi = cnt - 1;
         if ((uint32_t)(ch * SCHUNK + cnt) > warp_last) j_hi = (int)warp_last - ch * SCHUNK - 1;
         unsigned words[SCHUNK / 32];
-        classify_chunk(sp, j_hi + 1, lane, bxf, byf, words);  // j_hi < 0: nothing to do
+        classify_chunk(sp, j_hi + 1, lane, warp, all_blocks != 0, words);  // j_hi < 0: nothing to do
 #pragma unroll
         for (int k = SCHUNK / 32 - 1; k >= 0; k--) {
         unsigned word = words[k];
@@ -766,6 +761,13 @@ cudaError_t launch_surfel_project(int P, int sh_degree, int M, int W, int H, con
     return cudaGetLastError();
 }
 
+// GDR_SURFEL_MASKS=0: the blend kernels ignore the block masks and walk every record of the tile (read per launch,
+// so a test can compare both modes in one process)
+static int surfel_masks_off() {
+    const char* e = getenv("GDR_SURFEL_MASKS");
+    return (e && e[0] == '0') ? 1 : 0;
+}
+
 cudaError_t launch_surfel_blend_forward(int W, int H, ImageState img, const void* stream, int64_t capacity,
                                         const float* bg, float* out_color, float* out_allmap, float* aux,
                                         cudaStream_t s) {
@@ -774,7 +776,7 @@ cudaError_t launch_surfel_blend_forward(int W, int H, ImageState img, const void
                                          (int)sizeof(SurfelSmem));
     if (e != cudaSuccess) return e;
     surfel_blend_forward_kernel<<<gx * gy, SB_THREADS, sizeof(SurfelSmem), s>>>(
-        W, H, gx, gx * gy, img, (const Surfel*)stream, capacity, bg, out_color, out_allmap, aux);
+        W, H, gx, gx * gy, img, (const Surfel*)stream, capacity, bg, out_color, out_allmap, aux, surfel_masks_off());
     return cudaGetLastError();
 }
 
@@ -787,7 +789,8 @@ cudaError_t launch_surfel_blend_backward(int W, int H, ImageState img, const voi
                                          (int)sizeof(SurfelSmem));
     if (e != cudaSuccess) return e;
     surfel_blend_backward_kernel<<<gx * gy, SB_THREADS, sizeof(SurfelSmem), s>>>(
-        W, H, gx, gx * gy, img, (const Surfel*)stream, capacity, bg, out_allmap, aux, dL_dcolor, dL_dallmap, accum);
+        W, H, gx, gx * gy, img, (const Surfel*)stream, capacity, bg, out_allmap, aux, dL_dcolor, dL_dallmap, accum,
+        surfel_masks_off());
     return cudaGetLastError();
 }
 

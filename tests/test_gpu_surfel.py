@@ -272,3 +272,33 @@ def test_nan_mean_is_not_silently_dropped(device):
     assert bad["color"].shape == clean["color"].shape
     finite = torch.isfinite(bad["color"]).all(0)
     assert float(finite.float().mean()) > 0.5  # the NaN surfel's footprint is bounded by the tile clamp
+
+
+@pytest.mark.parametrize("size", ["scenes", "bench"])
+def test_block_masks_change_no_pixel(size, device, monkeypatch):
+    """tile_sort marks, per (surfel, tile) instance, which of the tile's eight 8x4 blocks the surfel can reach
+    (surfel_region_mask8: the exact conic of rho3d <= 2 ln(255 o) plus the low-pass disc) and the blend warps skip the
+    rest.  Skipped records fail the alpha test at every pixel of the block, so the images must be BIT-identical with
+    the masks ignored (GDR_SURFEL_MASKS=0), and the gradients equal up to the order of the float atomics."""
+    import diff_surfel_rasterization as D
+    from generativedensification_b200 import synthetic as S
+
+    if size == "scenes":
+        cases = [(SCENES[n], None) for n in SCENES]
+    else:
+        g = S.make_gaussians(200_000, 4321)
+        sc = dict(camera=S.orbit_cameras(4, 800, 800)[2], bg=torch.ones(3), sh_degree=1, scale_modifier=1.0,
+                  colors_precomp=None, **g)
+        cases = [(sc, None)]
+    for sc, _ in cases:
+        up = SU.surfel_upstream(sc)
+        monkeypatch.setenv("GDR_SURFEL_MASKS", "1")
+        a = SU.run_ours(sc, device, grads=up)
+        monkeypatch.setenv("GDR_SURFEL_MASKS", "0")
+        b = SU.run_ours(sc, device, grads=up)
+        assert torch.equal(a["color"], b["color"]) and torch.equal(a["allmap"], b["allmap"]), sc.get("name")
+        assert torch.equal(a["radii"], b["radii"])
+        for k in a:
+            if k.startswith("grad_") and a[k] is not None and a[k].numel():
+                scale = float(b[k].abs().max()) or 1.0
+                assert float((a[k] - b[k]).abs().max()) <= 2e-5 * scale, (sc.get("name"), k)
