@@ -106,3 +106,63 @@ def test_random_configuration_vs_compiled_reference(case, device):
         # the tensor's scale of float32 rounding in EITHER implementation -- both are deterministic there (cases 7 and
         # 28: 1.7e-3 / 1.2e-3 relative on one element each, 3e-6 / 1e-5 of the scale; tools/fuzz_diag.py).
         U.assert_grad_close(a, b, name=str((tag, k)), elem_atol=4e-6)
+
+
+N_BATCH_CASES = int(os.environ.get("GDR_FUZZ_BATCH_CASES", "16"))
+
+
+@pytest.mark.parametrize("case", range(N_BATCH_CASES))
+def test_random_batched_configuration_vs_compiled_reference(case, device):
+    """The opt-in entry points on random configurations: `render_images` over 1 .. 5 cameras of one batch, with the
+    activations and / or the render_img epilogue fused in at random, against Renderer.render_img's own sequence on the
+    compiled reference (torch activations, one reference call per view, clamp, permute) down to the raw parameters."""
+    from generativedensification_b200 import synthetic as S
+    from generativedensification_b200.views import render_images
+
+    ref = _ref()
+    rng = np.random.default_rng(7000 + case)
+    P = int(rng.choice([1, 40, 700, 5000, 30000]))
+    V = int(rng.integers(1, 6))
+    W, H = int(rng.integers(16, 261)), int(rng.integers(16, 261))
+    deg = int(rng.integers(0, 4))
+    fused_act, fused_epi = bool(rng.random() < 0.5), bool(rng.random() < 0.5)
+    gen = torch.Generator().manual_seed(100 + case)
+    act = S.make_gaussians(P, 300 + case, sh_degree=deg, log_scale_mean=float(rng.uniform(math.log(0.01), math.log(0.1))),
+                           opacity_logit_mean=float(rng.uniform(-2.0, 3.0)))
+    raw = dict(centers=act["means3D"], shs=act["shs"] * float(rng.uniform(0.5, 2.0)),
+               opacity=torch.logit(act["opacities"].clamp(1e-4, 1 - 1e-4)), scales=torch.log(act["scales"]),
+               rotations=act["rotations"] * (0.5 + torch.rand(P, 1, generator=gen)))
+    cams = [S.orbit_cameras(7, W, H)[i] for i in rng.choice(7, size=V, replace=False)]
+    bg = torch.tensor([float(x) for x in rng.random(3)])
+    g = torch.Generator().manual_seed(900 + case)
+    up = [(torch.randn(s, generator=g) / (H * W)).to(device) for s in ((V, H, W, 3), (V, H, W, 1), (V, H, W))]
+
+    def settings(mod, cam):
+        return mod.GaussianRasterizationSettings(
+            image_height=H, image_width=W, tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=bg.to(device),
+            scale_modifier=1.0, viewmatrix=cam["world_view_transform"].to(device),
+            projmatrix=cam["full_proj_transform"].to(device), sh_degree=deg, campos=cam["camera_center"].to(device),
+            prefiltered=False, debug=False)
+
+    lr = {k: v.to(device).clone().requires_grad_(True) for k, v in raw.items()}
+    imgs, deps, accs = [], [], []
+    for cam in cams:  # lightning/renderer.py:225-269
+        color, _, dep, acc = ref.GaussianRasterizer(settings(ref, cam))(
+            means3D=lr["centers"], means2D=torch.zeros(P, 4, device=device, requires_grad=True) + 0, shs=lr["shs"],
+            opacities=torch.sigmoid(lr["opacity"]), scales=torch.exp(lr["scales"]),
+            rotations=torch.nn.functional.normalize(lr["rotations"]))
+        imgs.append(color.clamp(0, 1).permute(1, 2, 0)); deps.append(dep.permute(1, 2, 0)); accs.append(acc.squeeze(0))
+    out_r = [torch.stack(imgs), torch.stack(deps), torch.stack(accs)]
+    grads_r = torch.autograd.grad(out_r, list(lr.values()), up)
+
+    import generativedensification_b200.rasterizer as ours
+    lo = {k: v.to(device).clone().requires_grad_(True) for k, v in raw.items()}
+    o = render_images([settings(ours, c) for c in cams], lo["centers"], lo["shs"], lo["opacity"], lo["scales"],
+                      lo["rotations"], fused_activations=fused_act, fused_epilogue=fused_epi)
+    grads = torch.autograd.grad([o["image"], o["depth"], o["acc_map"]], list(lo.values()), up)
+
+    tag = (case, P, V, W, H, deg, fused_act, fused_epi)
+    assert torch.equal(o["depth"], out_r[1]) and torch.equal(o["acc_map"], out_r[2]), tag
+    assert float((o["image"].detach() - out_r[0].detach()).abs().max()) <= 2e-6, tag
+    for name, a, b in zip(raw, grads, grads_r):
+        U.assert_grad_close(a, b, name=str((tag, name)), elem_atol=4e-6)
