@@ -302,3 +302,30 @@ def test_block_masks_change_no_pixel(size, device, monkeypatch):
             if k.startswith("grad_") and a[k] is not None and a[k].numel():
                 scale = float(b[k].abs().max()) or 1.0
                 assert float((a[k] - b[k]).abs().max()) <= 2e-5 * scale, (sc.get("name"), k)
+
+
+@pytest.mark.parametrize("case", range(int(__import__("os").environ.get("GDR_FUZZ_SURFEL_CASES", "24"))))
+def test_block_masks_change_no_pixel_on_random_configurations(case, device, monkeypatch):
+    """The block masks must be conservative everywhere: random sizes, anisotropies from discs to needles, surfels
+    that straddle the near plane (cameras pulled into the cloud: the conic of rho3d <= tau is then not an ellipse),
+    huge and tiny opacities -- forward maps bit-identical with the masks ignored."""
+    import numpy as np
+
+    rng = np.random.default_rng(4400 + case)
+    P = int(rng.choice([3, 60, 800, 6000]))
+    W, H = int(rng.integers(16, 200)), int(rng.integers(16, 200))
+    sc = SC._scene(f"sfuzz{case}", P, W, H, seed=800 + case, sh_degree=int(rng.integers(0, 4)),
+                   cam_index=int(rng.integers(0, 7)), n_cams=7, log_scale=float(rng.uniform(math.log(0.004), math.log(0.4))),
+                   opacity_mean=float(rng.uniform(-4.0, 5.0)), scale_modifier=float(rng.choice([1.0, 0.5, 3.0])))
+    gen = torch.Generator().manual_seed(case)
+    sc["scales"] = sc["scales"] * torch.exp(torch.randn(P, 3, generator=gen) * float(rng.uniform(0.0, 2.5)))  # anisotropy
+    if rng.random() < 0.5:  # pull the cloud around the camera: near-plane crossings, surfels seen edge-on from inside
+        eye = sc["camera"]["camera_center"]
+        sc["means3D"] = eye[None, :] + (sc["means3D"] - eye[None, :]) * float(rng.uniform(0.05, 0.6)) + \
+            0.3 * torch.randn(P, 3, generator=gen)
+    monkeypatch.setenv("GDR_SURFEL_MASKS", "1")
+    a = SU.run_ours(sc, device)
+    monkeypatch.setenv("GDR_SURFEL_MASKS", "0")
+    b = SU.run_ours(sc, device)
+    same = lambda x, y: torch.equal(torch.nan_to_num(x, nan=-7.0), torch.nan_to_num(y, nan=-7.0))
+    assert same(a["color"], b["color"]) and same(a["allmap"], b["allmap"]), (case, P, W, H)
