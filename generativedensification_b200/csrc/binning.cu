@@ -29,11 +29,15 @@ namespace {
 #define GDR_SORT_THREADS 256
 #endif
 constexpr int SORT_THREADS = GDR_SORT_THREADS;
-constexpr int SORT_CHUNK = 4096;  // keys per shared-memory sort (32 KB)
+// Keys per shared-memory sort (8 bytes each) come in two sizes, chosen per launch from the frame's tile capacity:
+// 2048 (16 KB: 8 CTAs per SM) when the densest tile is expected below ~2000 instances -- lists up to 1024 sort in
+// shared memory, the few longer ones through global memory -- and 4096 (32 KB: 5 CTAs per SM) for dense frames, whose
+// long-list path then gets 4096 depth buckets instead of 2048 (measured: 29 vs 33 us at the 200k / 800^2 benchmark
+// frame with the small buffer, 745 vs 672 us at 2M / 1600^2).
+constexpr int SORT_CHUNK_SMALL = 2048, SORT_CHUNK_LARGE = 4096;
 constexpr int BUCKET_BITS = 10;
 constexpr int BUCKETS = 1 << BUCKET_BITS;   // depth buckets of the per-tile bucket sort
 constexpr int BUCKET_MIN = 65;              // shorter lists: the bitonic network is already cheap
-constexpr int BUCKET_MAX = SORT_CHUNK / 2;  // the grouped copy lives in the second half of the key buffer
 constexpr int BUCKET_MAX_FILL = 48;         // largest bucket the quadratic in-bucket ranking accepts
 static_assert(BUCKETS % SORT_THREADS == 0, "bucket scan assigns BUCKETS / SORT_THREADS buckets per thread");
 
@@ -53,7 +57,7 @@ __device__ __forceinline__ void bitonic_cmpxchg(uint64_t* s, int i, int j, int k
 // Sub-stages with partner distance j <= 32 only exchange elements inside aligned 64-element blocks, so a
 // warp that owns a block runs all of them back to back with warp-level synchronisation; only the
 // sub-stages with j >= 64 need the CTA barrier (6 instead of 45 barriers for a 512-entry tile list).
-__device__ __forceinline__ void bitonic_sort_smem(uint64_t* s, int n_pad) {
+__device__ __forceinline__ void bitonic_sort_smem(uint64_t* s, int n_pad) {  // n_pad <= the caller's key buffer
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int N_WARPS = SORT_THREADS / 32;
     const int n_blocks = max(n_pad >> 6, 1);  // 64-element blocks (a single partial block when n_pad < 64)
@@ -84,11 +88,14 @@ __device__ __forceinline__ int lower_bound_u64(const uint64_t* a, int n, uint64_
 }
 
 // RQ = 128-bit words per record: 3 for the 48-byte Splat, 5 for the 80-byte Surfel (surfel.cuh).
-template <int RQ>
+template <int RQ, int SORT_CHUNK>
 __global__ void __launch_bounds__(SORT_THREADS)
 tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t* keys0, float4* __restrict__ stream0,
                  int64_t capacity, uint32_t tile_cap, const uint32_t* __restrict__ tile_base0, size_t keys_stride,
                  size_t geom_stride, size_t img_stride, int gx, int T) {
+    constexpr int BUCKET_MAX = SORT_CHUNK / 2;  // the grouped copy lives in the second half of the key buffer
+    constexpr int BIG_BITS = SORT_CHUNK >= 4096 ? 12 : 11;  // long lists: counters + scan alias the key buffer
+    static_assert((2 << BIG_BITS) * 4 <= SORT_CHUNK * 8, "the long-list counters live in the key buffer");
     __shared__ uint64_t s_keys[SORT_CHUNK];
     __shared__ uint32_t s_cnt[BUCKETS];        // bucket histogram, then fill cursors
     __shared__ uint32_t s_start[BUCKETS + 1];  // exclusive scan of the histogram
@@ -154,7 +161,7 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
     // plus the in-bucket ranking replace a 4096-entry bitonic network per chunk and log2(n / 4096) merge passes.
     bool sorted_big = false;
     if (n > BUCKET_MAX) {
-        constexpr int NBIG = 4096;
+        constexpr int NBIG = 1 << BIG_BITS;
         uint32_t* big_cnt = reinterpret_cast<uint32_t*>(s_keys);  // [NBIG] histogram, then fill cursors
         uint32_t* big_start = big_cnt + NBIG;                     // [NBIG] exclusive scan
         uint64_t* grouped = alt;
@@ -179,7 +186,7 @@ tile_sort_kernel(const float4* __restrict__ records0, ImageState img0, uint64_t*
         }
         __syncthreads();
         const uint32_t dmin = s_misc[0], range = s_misc[1] - s_misc[0];
-        const int sh = max(0, (32 - __clz(range)) - 12);  // (d - dmin) >> sh < NBIG
+        const int sh = max(0, (32 - __clz(range)) - BIG_BITS);  // (d - dmin) >> sh < NBIG
         for (int i = threadIdx.x; i < n; i += SORT_THREADS)
             atomicAdd(&big_cnt[((uint32_t)(seg[i] >> 32) - dmin) >> sh], 1u);
         __syncthreads();
@@ -436,6 +443,16 @@ size_t key_bytes_per_view(int W, int H, int64_t tile_cap, bool exact) {
     return exact ? align_up((size_t)tile_cap * sizeof(uint64_t), 256) : sort_scratch_bytes(W, H, tile_cap);
 }
 
+// The uniform layout's tile capacity is the host's forecast of the densest tile (2x the previous frame's + 256): up to
+// 4096 slots the frame is a sparse one.  The exact layout (a frame whose forecast failed, or a degenerate distribution)
+// always takes the large buffer.
+#ifndef GDR_SORT_SMALL_CAP
+#define GDR_SORT_SMALL_CAP 4096
+#endif
+static bool small_sort_buffer(int64_t tile_cap, const uint32_t* tile_base) {
+    return tile_base == nullptr && tile_cap <= GDR_SORT_SMALL_CAP;
+}
+
 cudaError_t launch_tile_offsets(int W, int H, ImageState img, uint32_t* tile_offsets, const Views& vw, cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     tile_offsets_kernel<<<max(1, vw.V), 1024, 0, s>>>(gx * gy, img, vw.img_stride, tile_offsets);
@@ -446,21 +463,29 @@ cudaError_t launch_tile_sort(int W, int H, GeomState geom, ImageState img, uint6
                              const uint32_t* tile_base, Splat* stream, int64_t capacity, const Views& vw,
                              cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    return launch_dependent(tile_sort_kernel<3>, dim3(gx * gy, max(1, vw.V)), dim3(SORT_THREADS), 0, s,
-                            reinterpret_cast<const float4*>(geom.splat), img, keys, reinterpret_cast<float4*>(stream),
-                            capacity, (uint32_t)tile_cap, tile_base,
-                            key_bytes_per_view(W, H, tile_cap, tile_base != nullptr) / sizeof(uint64_t), vw.geom_stride,
-                            vw.img_stride, gx, gx * gy);
+    auto launch = [&](auto kernel) {
+        return launch_dependent(kernel, dim3(gx * gy, max(1, vw.V)), dim3(SORT_THREADS), 0, s,
+                                reinterpret_cast<const float4*>(geom.splat), img, keys, reinterpret_cast<float4*>(stream),
+                                capacity, (uint32_t)tile_cap, tile_base,
+                                key_bytes_per_view(W, H, tile_cap, tile_base != nullptr) / sizeof(uint64_t),
+                                vw.geom_stride, vw.img_stride, gx, gx * gy);
+    };
+    return small_sort_buffer(tile_cap, tile_base) ? launch(tile_sort_kernel<3, SORT_CHUNK_SMALL>)
+                                                  : launch(tile_sort_kernel<3, SORT_CHUNK_LARGE>);
 }
 
 cudaError_t launch_tile_sort_surfel(int W, int H, const void* surfel_records, ImageState img, uint64_t* keys,
                                     int64_t tile_cap, const uint32_t* tile_base, void* surfel_stream, int64_t capacity,
                                     cudaStream_t s) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    return launch_dependent(tile_sort_kernel<5>, dim3(gx * gy, 1), dim3(SORT_THREADS), 0, s,
-                            reinterpret_cast<const float4*>(surfel_records), img, keys,
-                            reinterpret_cast<float4*>(surfel_stream), capacity, (uint32_t)tile_cap, tile_base, (size_t)0,
-                            (size_t)0, (size_t)0, gx, gx * gy);
+    auto launch = [&](auto kernel) {
+        return launch_dependent(kernel, dim3(gx * gy, 1), dim3(SORT_THREADS), 0, s,
+                                reinterpret_cast<const float4*>(surfel_records), img, keys,
+                                reinterpret_cast<float4*>(surfel_stream), capacity, (uint32_t)tile_cap, tile_base,
+                                (size_t)0, (size_t)0, (size_t)0, gx, gx * gy);
+    };
+    return small_sort_buffer(tile_cap, tile_base) ? launch(tile_sort_kernel<5, SORT_CHUNK_SMALL>)
+                                                  : launch(tile_sort_kernel<5, SORT_CHUNK_LARGE>);
 }
 
 }  // namespace gdr
