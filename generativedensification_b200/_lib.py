@@ -21,6 +21,7 @@ GDR_OK = 0
 GRAD_MEANS2D, GRAD_MEANS3D, GRAD_COLOR, GRAD_OPACITY, GRAD_COV, GRAD_ALL = 1, 2, 4, 8, 16, 31
 GRAD_RAW_PARAMS = 32
 GRAD_HWC_COLOR = 64
+GRAD_SCRATCH_CLEAN = 128
 FLAG_NO_TILE_CULL = 1
 FLAG_RAW_PARAMS = 2
 FLAG_RERUN = 4

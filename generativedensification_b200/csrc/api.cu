@@ -267,7 +267,8 @@ int backward_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, i
     gdr::ImageState img = gdr::ImageState::carve(const_cast<void*>(image_state), W, H);
     gdr::GeomState geom = gdr::GeomState::carve(const_cast<void*>(geom_state), (size_t)P);
     float* accum = (float*)backward_scratch;
-    GDR_CUDA(cudaMemsetAsync(accum, 0, sizeof(float) * 12 * (size_t)P * (size_t)vw.V, s), "memset(accum)");
+    const bool clean = (grad_mask & GDR_GRAD_SCRATCH_CLEAN) != 0;  // the caller's buffer is zeroed and stays so
+    if (!clean) GDR_CUDA(cudaMemsetAsync(accum, 0, sizeof(float) * 12 * (size_t)P * (size_t)vw.V, s), "memset(accum)");
     {
         StageTimer t(GDR_STAGE_BLEND_BWD, s);
         GDR_CUDA(gdr::launch_blend_backward(P, W, H, img, (const gdr::Splat*)splat_stream, capacity, out_alpha,
@@ -279,7 +280,7 @@ int backward_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, i
     a.means3D = g.means3D; a.shs = g.shs; a.colors_precomp = g.colors_precomp; a.scales = g.scales;
     a.scale_modifier = g.scale_modifier; a.rotations = g.rotations; a.cov3D_precomp = g.cov3D_precomp;
     a.vw = vw;
-    a.radii = radii; a.geom = geom; a.accum = accum; a.grad_mask = grad_mask;
+    a.radii = radii; a.geom = geom; a.accum = accum; a.grad_mask = grad_mask; a.rezero = clean ? 1 : 0;
     a.dL_dmeans2D = o.means2D; a.dL_dcolors = o.colors; a.dL_dopacity = o.opacity;
     a.dL_dmeans3D = o.means3D; a.dL_dcov3D = o.cov3D; a.dL_dsh = o.sh; a.dL_dscales = o.scales;
     a.dL_drotations = o.rotations;

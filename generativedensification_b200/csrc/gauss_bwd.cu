@@ -426,6 +426,15 @@ __global__ void __launch_bounds__(GB_THREADS, GDR_GB_MINB) gauss_backward_kernel
             __syncthreads();
         }
         if (in_range) gauss_backward_one<ACC>(a, rows, idx, visible, q_in, clamp_in, opacity_in);
+        // GDR_GRAD_SCRATCH_CLEAN: the accumulator rows go back to zero once consumed, so the caller's buffer needs no
+        // fill before its next backward (a 9.6 MB memset per view at 200k Gaussians, and a launch boundary).  Each
+        // thread has read its own row by now; full blocks leave as one bulk store of the zeroed rows, others directly.
+        float* acc_dst = a.accum + ((size_t)vi * a.P + first) * 12;
+        const bool rezero_bulk = a.rezero && need_rows && bulk;
+        if (a.rezero && in_range) {
+            float4* z = reinterpret_cast<float4*>(rezero_bulk ? rows.acc + 12 * threadIdx.x : acc_dst + 12 * threadIdx.x);
+            z[0] = z[1] = z[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         // ---- the outputs with a 12- / 24- / 48-byte row stride leave coalesced ----
         if (need_rows) {
             if (bulk) {
@@ -439,6 +448,7 @@ __global__ void __launch_bounds__(GB_THREADS, GDR_GB_MINB) gauss_backward_kernel
                     if (a.dL_dscales) out(a.dL_dscales + (size_t)first * 3, rows.scale, 3 * ROW);
                     if (a.dL_dcov3D) out(a.dL_dcov3D + (size_t)first * 6, rows.cov, 6 * ROW);
                     if (a.dL_dsh) out(a.dL_dsh + (size_t)first * 3 * M, rows.sh, 3 * M * ROW);
+                    if (rezero_bulk) bulk_s2g(acc_dst, rows.acc, 12 * ROW);
                     bulk_commit();
                     bulk_wait_read();  // the rows may be overwritten (next virtual block) once they have been read
                 }

@@ -104,8 +104,9 @@ struct GaussBackwardArgs {
     int accumulate;    // 0: store the outputs; 1: add to them (views 1.. of a batch: gradients sum over views)
     const int32_t* radii;  // [V][P]
     GeomState geom;
-    const float* accum;    // [V][P][12]
+    float* accum;          // [V][P][12]; read, and re-zeroed when `rezero` is set
     int grad_mask;
+    int rezero;        // store zeros back over the accumulator rows after reading them (GDR_GRAD_SCRATCH_CLEAN)
     float* dL_dmeans2D;
     float* dL_dcolors;
     float* dL_dopacity;

@@ -274,6 +274,34 @@ def _scratch(device, stream, nbytes: int) -> torch.Tensor:
     return t
 
 
+_accum_cache = {}
+CLEAN_ACCUMULATORS = os.environ.get("GDR_CLEAN_ACCUM", "1") != "0"  # 0: a fresh buffer and a fill per backward
+
+
+def _clean_accumulators(device, stream, nbytes: int) -> torch.Tensor:
+    """The backward's screen-space accumulators, one grow-only buffer per (device, stream) that is zero-filled ONCE: with
+    GDR_GRAD_SCRATCH_CLEAN the per-Gaussian kernel stores zeros back over every row it consumed, so consecutive
+    backwards of a stream (they are ordered) share the buffer without a fill per call.  A backward that raises must
+    hand the buffer back through _drop_accumulators: its state is unknown then."""
+    k = (device.index, stream.cuda_stream)
+    t = _accum_cache.get(k)
+    if t is None or t.numel() < nbytes:
+        t = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _accum_cache[k] = t
+    return t
+
+
+def _accumulators(device, stream, nbytes: int):
+    """(buffer, grad_mask bits) for one backward."""
+    if CLEAN_ACCUMULATORS:
+        return _clean_accumulators(device, stream, nbytes), _lib.GRAD_SCRATCH_CLEAN
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), 0
+
+
+def _drop_accumulators(device, stream) -> None:
+    _accum_cache.pop((device.index, stream.cuda_stream), None)
+
+
 class _ForwardState:
     """Opaque state kept between forward and backward (the reference keeps three byte tensors)."""
     __slots__ = ("geom", "img", "stream_buf", "capacity", "num_rendered", "P", "M")
@@ -406,16 +434,21 @@ def _backward_impl(settings, st: _ForwardState, saved, grad_color, grad_depth, g
         grad_color = _f32c(grad_color, device)
         grad_depth = None if grad_depth is None else _f32c(grad_depth, device)
         grad_alpha = None if grad_alpha is None else _f32c(grad_alpha, device)
-        scratch = torch.empty(_lib.query_bytes("gdr_backward_scratch_bytes", P), dtype=torch.uint8, device=device)
-        sptr = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        _lib.check(lib.gdr_backward(
+        stream = torch.cuda.current_stream(device)
+        scratch, clean_bit = _accumulators(device, stream, _lib.query_bytes("gdr_backward_scratch_bytes", P))
+        mask |= clean_bit
+        sptr = C.c_void_p(stream.cuda_stream)
+        status = lib.gdr_backward(
             P, int(settings.sh_degree), M, W, H, bg_p, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(scales),
             float(settings.scale_modifier), _ptr(rotations), _ptr(cov3Ds_precomp), view_p, proj_p, campos_p,
             float(settings.tanfovx), float(settings.tanfovy), radii.data_ptr(), st.geom.data_ptr(), st.img.data_ptr(),
             _ptr(st.stream_buf), st.capacity, alpha.data_ptr(), grad_color.data_ptr(), _ptr(grad_depth),
             _ptr(grad_alpha), scratch.data_ptr(), mask, _ptr(out["means2D"]), _ptr(out["colors"]),
             _ptr(out["opacity"]), _ptr(out["means3D"]), _ptr(out["cov3D"]), _ptr(out["sh"]), _ptr(out["scales"]),
-            _ptr(out["rot"]), sptr), "gdr_backward")
+            _ptr(out["rot"]), sptr)
+        if status != _lib.GDR_OK:
+            _drop_accumulators(device, stream)  # whatever was enqueued may have left sums behind
+        _lib.check(status, "gdr_backward")
     return out
 
 

@@ -25,8 +25,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .rasterizer import (PREFILTERED_MESSAGE, GaussianRasterizationSettings, _f32c, _mailbox, _ptr, _scratch,
-                         drive_forward, options)
+from .rasterizer import (PREFILTERED_MESSAGE, GaussianRasterizationSettings, _accumulators, _drop_accumulators,
+                         _f32c, _mailbox, _ptr, _scratch, drive_forward, options)
 
 
 class CameraBatch:
@@ -198,15 +198,21 @@ def _backward_views(cb: CameraBatch, st: _ViewsState, saved, grad_color, grad_de
         grad_color = _f32c(grad_color, device)
         grad_depth = None if grad_depth is None else _f32c(grad_depth, device)
         grad_alpha = None if grad_alpha is None else _f32c(grad_alpha, device)
-        scratch = torch.empty(_lib.query_bytes("gdr_backward_scratch_bytes", V * P), dtype=torch.uint8, device=device)
-        sptr = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        _lib.check(lib.gdr_views_backward(
+        stream = torch.cuda.current_stream(device)
+        # the same zero-filled-once accumulator buffer as the single-view path (rasterizer._clean_accumulators)
+        scratch, clean_bit = _accumulators(device, stream, _lib.query_bytes("gdr_backward_scratch_bytes", V * P))
+        mask |= clean_bit
+        sptr = C.c_void_p(stream.cuda_stream)
+        status = lib.gdr_views_backward(
             V, P, cb.sh_degree, M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(scales),
             cb.scale_modifier, _ptr(rotations), _ptr(cov3Ds_precomp), cb.cams.data_ptr(), radii.data_ptr(),
             st.geom.data_ptr(), st.img.data_ptr(), _ptr(st.stream_buf), st.capacity, alpha.data_ptr(),
             grad_color.data_ptr(), _ptr(grad_depth), _ptr(grad_alpha), scratch.data_ptr(), mask,
             _ptr(out["means2D"]), _ptr(out["colors"]), _ptr(out["opacity"]), _ptr(out["means3D"]), _ptr(out["cov3D"]),
-            _ptr(out["sh"]), _ptr(out["scales"]), _ptr(out["rot"]), sptr), "gdr_views_backward")
+            _ptr(out["sh"]), _ptr(out["scales"]), _ptr(out["rot"]), sptr)
+        if status != _lib.GDR_OK:
+            _drop_accumulators(device, stream)
+        _lib.check(status, "gdr_views_backward")
     return out
 
 

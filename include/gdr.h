@@ -85,6 +85,12 @@ extern "C" {
                                   the clamped image); no gradient flows through a channel the clamp cut, as with
                                   torch.clamp */
 
+#define GDR_GRAD_SCRATCH_CLEAN 128 /* gdr_backward / gdr_views_backward: backward_scratch holds zeros on entry (a buffer the
+                                  caller keeps per stream, zero-filled once).  The call then skips its own fill, and the
+                                  per-Gaussian kernel stores zeros back over every accumulator row after consuming it, so
+                                  the buffer holds zeros again when the enqueued work has run.  A call that FAILS leaves
+                                  the buffer in an unknown state: zero-fill it (or drop it) before the next use. */
+
 /* flags for gdr_forward_project / gdr_forward_render (must be identical in both calls of a frame) */
 #define GDR_FLAG_NO_TILE_CULL 1 /* bin every tile of the reference's 3-sigma rectangle, exactly like the reference.
                                    Default (0): drop (Gaussian, tile) pairs that provably cannot reach

@@ -507,3 +507,48 @@ def test_nan_mean_follows_the_reference(device):
         assert torch.equal(a, b)  # the image is the scene without that Gaussian: no NaN leaks in
     vis = rast.markVisible(bad)
     assert bool(vis[5])  # NaN <= 0.2 is false: "visible", as in the reference
+
+
+def test_shared_backward_accumulators_stay_clean(device):
+    """GDR_GRAD_SCRATCH_CLEAN: the backward's accumulator buffer is zero-filled once per stream and every backward
+    leaves it zeroed (the per-Gaussian kernel re-zeroes the rows it consumed).  Backwards of different scenes, sizes,
+    gradient subsets and entry points share it: each must give what it gives with a buffer of its own, and the buffer
+    must hold zeros whenever the stream is idle."""
+    from generativedensification_b200 import rasterizer as Rz
+    from generativedensification_b200 import synthetic as S
+    from generativedensification_b200.views import MultiViewRasterizer
+
+    def grads_of(sc, subset=None):
+        return U.run_ours(sc, device, grads=SC.upstream_grads(sc), with_state=False)
+
+    def buffer_is_zero():
+        torch.cuda.synchronize(device)
+        bufs = [t for (d, _), t in Rz._accum_cache.items() if d == device.index]
+        assert bufs, "no accumulator buffer was created"
+        return all(int(t.view(torch.int32).count_nonzero()) == 0 for t in bufs)
+
+    scenes = [SC._scene("acc_a", 5000, 200, 160, 71, sh_degree=2), SC._scene("acc_b", 777, 96, 100, 72, sh_degree=0),
+              SC._scene("acc_c", 12000, 128, 128, 73, sh_degree=3, colors_precomp=False, cov_precomp=True),
+              SC._scene("acc_d", 300, 64, 64, 74, colors_precomp=True)]
+    fresh = []
+    for sc in scenes:  # each with a buffer of its own
+        Rz._accum_cache.clear()
+        fresh.append(grads_of(sc))
+        assert buffer_is_zero()
+    Rz._accum_cache.clear()
+    for rounds in range(2):  # now sharing one buffer, largest scene not first
+        for sc, ref in zip(scenes, fresh):
+            out = grads_of(sc)
+            for k in ref:
+                if k.startswith("grad_") and ref[k].size:
+                    U.assert_grad_close(out[k], ref[k], name=(sc["name"], k), tol=2e-5, elem_rtol=1e-4, elem_atol=4e-6)
+            assert buffer_is_zero(), sc["name"]
+    # the means2D-only vjp (densify) and the batched entry point go through the same buffer
+    g = {k: v.to(device) for k, v in S.make_gaussians(4000, 75).items()}
+    cams = S.orbit_cameras(3, 96, 96)
+    m2 = torch.zeros(4000, 4, device=device, requires_grad=True)
+    rast = MultiViewRasterizer([S.settings_for(c, torch.ones(3), 1, device) for c in cams])
+    color, _, _, _ = rast(means3D=g["means3D"], means2D=m2, opacities=g["opacities"], shs=g["shs"], scales=g["scales"],
+                          rotations=g["rotations"])
+    color.square().mean().backward()
+    assert float(m2.grad.abs().max()) > 0 and buffer_is_zero()
