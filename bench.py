@@ -607,7 +607,8 @@ def main():
                                  "(--config 4) is the one whose consumer is the host."},
                     l2_warm={"value": per_step(warm_ms), "ms_per_step": warm_ms / a.steps,
                              "note": "the same steps without the L2 flush between them"},
-                    gpu_launches=(3 + (0 if a.forward_only else 2)) * len(cams) * a.steps,
+                    gpu_launches=(4 + (0 if a.forward_only else 2)) * len(cams) * a.steps,  # zero_state, project, tile_sort,
+                    # blend_forward (+ blend_backward, gauss_backward) per view
                     roofline={"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                               "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": measured_traffic(dominant, a),
                               "peak_source": ("MEASURED_PEAKS.json hbm_gbs (driver-measured copy bandwidth of this pool's B200s)"

@@ -167,13 +167,9 @@ int project_impl(const char* who, const gdr::Views& vw, int P, int sh_degree, in
     }
     gdr::ImageState img = gdr::ImageState::carve(image_state, W, H);
     const int T = tiles_of(W, H);
-    // header and per-tile slot counters are adjacent: one memset (strided over the views of a batch)
-    const size_t zero_bytes = (size_t)((char*)(img.tile_count + (size_t)T * gdr::COUNT_STRIDE) - (char*)img.header);
-    if (vw.V == 1)
-        GDR_CUDA(cudaMemsetAsync(img.header, 0, zero_bytes, s), "memset(header, tile_count)");
-    else
-        GDR_CUDA(cudaMemset2DAsync(img.header, vw.img_stride, 0, zero_bytes, (size_t)vw.V, s),
-                 "memset(header, tile_count)");
+    // header and per-tile slot counters are adjacent: one zeroing launch for all views, which the projection kernel
+    // follows as a programmatic dependent (project.cu)
+    GDR_CUDA(gdr::launch_zero_state(img, W, H, vw, s), "zero(header, tile_count)");
     if (P > 0) {
         gdr::ProjectArgs a;
         a.P = P; a.sh_degree = sh_degree; a.M = M; a.W = W; a.H = H;

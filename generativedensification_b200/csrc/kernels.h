@@ -59,6 +59,8 @@ struct ProjectArgs {
 
 // project.cu: per-Gaussian projection + warp-aggregated tile counting
 cudaError_t launch_project(const ProjectArgs& a, cudaStream_t s);
+// zeroes the header + slot counters of every view; launch_project's kernel is its programmatic dependent
+cudaError_t launch_zero_state(ImageState img, int W, int H, const Views& vw, cudaStream_t s);
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                                 cudaStream_t s);
 

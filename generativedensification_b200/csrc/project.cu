@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, GDR_PROJ_MINB) project_kernel(co
                 }
             }
         } else if (a.prefiltered) {
+            pdl_wait();  // the header is being zeroed by the launch before this one (see launch_project)
             atomicOr(&img.header[HDR_PROJECT_FLAGS], HDR_FLAG_PREFILTERED);  // the reference traps here (auxiliary.h:154-158);
                                                                      // we flag, the host raises
         }
@@ -320,6 +321,10 @@ __global__ void __launch_bounds__(PROJ_THREADS, GDR_PROJ_MINB) project_kernel(co
     // ---- bin the instances: claim a slot of the tile's key segment per kept (Gaussian, tile) pair ----
     // With culling on, a pair is only binned if the splat can reach alpha >= 1/255 somewhere in the tile
     // (exact: see splat_misses_rect in common.cuh).
+    // Everything above touched neither the header nor the slot counters: this launch is a programmatic dependent of the
+    // kernel that zeroes them (zero_state_kernel), so the staging and the projection arithmetic overlap it; the
+    // claims need the zeros.
+    pdl_wait();
     EmitRec* s_rec = reinterpret_cast<EmitRec*>(smem + emit_offset_words) + (threadIdx.x & ~31u);
     const uint32_t depth_bits = __float_as_uint(rec.q2.w);
     if (a.cull)
@@ -344,6 +349,16 @@ __global__ void __launch_bounds__(PROJ_THREADS, GDR_PROJ_MINB) project_kernel(co
         if (a.counts_host) report_counts(img.header, a.counts_host + 4 * v, gridDim.x);
     }
     pdl_trigger();  // tile_sort may start launching
+}
+
+// Zeroes the header and the per-tile slot counters of every view (they are adjacent in ImageState): a kernel rather
+// than a memset node so that the projection kernel can be launched as its programmatic dependent -- it releases the
+// dependent at once, and the projection only waits for it where it first needs the zeros.
+__global__ void __launch_bounds__(256) zero_state_kernel(uint4* __restrict__ base, size_t n16, size_t view_stride_bytes) {
+    pdl_trigger();
+    uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<char*>(base) + (size_t)blockIdx.y * view_stride_bytes);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
@@ -390,7 +405,17 @@ cudaError_t launch_project(const ProjectArgs& a, cudaStream_t s) {
         per_sm = 1;
     const int V = max(1, a.vw.V);
     const int grid = min(n_vblocks, max(1, sm_count() * per_sm / V));  // one balanced wave over all views
-    project_kernel<<<dim3(grid, V), PROJ_THREADS, smem, s>>>(a);
+    return launch_dependent(project_kernel, dim3(grid, V), dim3(PROJ_THREADS), smem, s, a);
+}
+
+cudaError_t launch_zero_state(ImageState img, int W, int H, const Views& vw, cudaStream_t s) {
+    const size_t T = ImageState::tiles(W, H);
+    const size_t bytes = (size_t)((char*)(img.tile_count + T * COUNT_STRIDE) - (char*)img.header);  // a multiple of 256
+    const size_t n16 = bytes / sizeof(uint4);
+    const int V = max(1, vw.V);
+    const size_t blocks = (n16 + 255) / 256, cap = (size_t)sm_count() * 4;
+    const int grid = (int)(blocks < cap ? blocks : cap);
+    zero_state_kernel<<<dim3(grid, V), 256, 0, s>>>(reinterpret_cast<uint4*>(img.header), n16, vw.img_stride);
     return cudaGetLastError();
 }
 
