@@ -207,6 +207,7 @@ blend_forward_kernel(int W, int H, int gx, int T, ImageState img0, const Splat* 
     };
     if (inside_a) write_pixel(pya, C0a, C1a, C2a, Ta, wa, Da, last_a);
     if (inside_b) write_pixel(pyb, C0b, C1b, C2b, Tb, wb, Db, last_b);
+    pdl_trigger();  // a backward blend enqueued right behind this launch may start launching (it waits for our stores)
 }
 
 }  // namespace
